@@ -1,0 +1,267 @@
+// grayshift_b200/csrc/gs_device.cuh -- device-side data layout, RNG, intersection and BVH traversal
+// shared by the render megakernel (render_kernels.cu) and the parity kernel (trace_closest.cu,
+// compiled with -fmad=false).  sm_100a only.
+//
+// Layout in HBM (all immutable after gs_scene_create; C1-C4 working sets are L1/L2 resident,
+// C5 ~100 MB fits the 126 MB L2):
+//   nodes     DNode[ ]     64 B, two child boxes per node (fp32, padded outward), 4 x 128-bit loads
+//   refs      uint32[ ]    leaf -> primitive references, kind<<30 | index, leaf order
+//   spheres   DSphere[ ]   32 B f64 (cx,cy,cz,r; r<0 flags a moving sphere), leaf order, 2 x 128-bit loads
+//   sph_path  double4[ ]   only read for moving spheres
+//   quads     DQuad[ ]     96 B f64 (plane n,d; barycentric functionals A,qa,B,qb), 6 x 128-bit loads
+//   *_aux     int2[ ]      (material, prim_id) per primitive, read once per accepted hit
+//   materials/textures     32 B records; images as uchar4 / float4 texels (one 32/128-bit load per lookup)
+//
+// Precision: boxes are tested in fp32 against conservatively padded bounds; primitives are
+// intersected in f64 with the reference's formulas (B200 keeps a half-rate FP64 pipe and the
+// reference is f64 throughout: ground sphere r=1000, t_min=0.001); shading is fp32.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gs {
+
+// ------------------------------------------------------------------------------------------
+// Records
+// ------------------------------------------------------------------------------------------
+struct __align__(16) DNode {
+	float4 xy0;  // child 0: min.x, max.x, min.y, max.y
+	float4 xy1;  // child 1
+	float4 z01;  // c0.min.z, c0.max.z, c1.min.z, c1.max.z
+	int4 link;   // child0, child1 (>= 0 internal node index; < 0 leaf code), unused, unused
+};
+// leaf code: -1 - ((first_ref << 4) | count), count <= 15
+__host__ __device__ inline int leaf_code(uint32_t first, uint32_t count) { return -1 - (int)((first << 4) | count); }
+constexpr int kStackSentinel = 0x7fffffff;
+constexpr int kMaxStack = 64;
+
+struct __align__(16) DSphere { double cx, cy, cz, r; };  // r < 0: moving, |r| is the radius
+struct __align__(16) DQuad {
+	double nx, ny, nz, d;    // unit plane normal and offset (quad.rs:32-36, plane.rs:15-18)
+	double ax, ay, az, qa;   // alpha = P.A - qa with A = v x w    (== w . (planar x v), quad.rs:88)
+	double bx, by, bz, qb;   // beta  = P.B - qb with B = w x u    (== w . (u x planar), quad.rs:89)
+};
+struct __align__(16) DMaterial { int kind; int tex; float ar, ag, ab; float param; int pad0, pad1; };
+struct __align__(16) DTexture { int kind; int a; int b; float scale; float cr, cg, cb; float pad; double scale_inv_d; double scale_d; };
+struct DImage { int w, h; int format; int pad; const void* texels; };  // uchar4 (u8) or float4 (f32) texels, row 0 = top
+struct DMedium { int sph_first, sph_count, quad_first, quad_count; double neg_inv_density; int phase_mat; int index; };
+
+constexpr uint32_t kRefKindShift = 30;
+constexpr uint32_t kRefIndexMask = (1u << 30) - 1u;
+
+struct DeviceScene {
+	const DNode* nodes;
+	const uint32_t* refs;
+	const DSphere* spheres;
+	const double4* sph_path;
+	const int2* sph_aux;
+	const DQuad* quads;
+	const int2* quad_aux;
+	const int* quad_order;  // reference visiting rank, read only on exact-t ties
+	const DSphere* bnd_spheres;
+	const double4* bnd_sph_path;
+	const DQuad* bnd_quads;
+	const DMedium* media;
+	const DMaterial* materials;
+	const DTexture* textures;
+	const DImage* images;
+	const uint8_t* perlin_perm;
+	int n_media;
+	int root;  // node index or leaf code
+};
+
+struct DCamera {
+	double center[3], pixel00[3], du[3], dv[3], disk_u[3], disk_v[3];
+	double defocus_angle;
+	int width, height;
+	unsigned max_depth;
+	int bg_kind;
+	float bg[3];
+	int hdri_image;
+	float rot[9];  // rotate_vector's matrix (util.rs:67-86), rows x,y,z
+};
+
+// ------------------------------------------------------------------------------------------
+// Philox4x32-10, counter = (pixel, sample, block, stream), key = seed.  Draw k of a path is
+// word k&3 of block k>>2 (the oracle uses the identical scheme).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+	for (int r = 0; r < 10; ++r) {
+		uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+		uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+		uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+		c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+		k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+	}
+	return make_uint4(c0, c1, c2, c3);
+}
+
+struct PathRng {
+	uint32_t pixel, sample, draw, k0, k1;
+	uint4 buf;
+	__device__ __forceinline__ void start(uint64_t seed, uint32_t pixel_, uint32_t sample_) {
+		pixel = pixel_; sample = sample_; draw = 0; k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32);
+	}
+	__device__ __forceinline__ uint32_t next_u32() {
+		uint32_t w = draw & 3u;
+		if (w == 0) buf = philox4x32_10(pixel, sample, draw >> 2, 0u, k0, k1);
+		++draw;
+		return w == 0 ? buf.x : (w == 1 ? buf.y : (w == 2 ? buf.z : buf.w));
+	}
+	__device__ __forceinline__ float next_f32() { return (float)(next_u32() >> 8) * (1.0f / 16777216.0f); }  // [0,1), 24 bits
+	__device__ __forceinline__ double next_f64() { return (double)next_u32() * (1.0 / 4294967296.0); }       // the oracle's value exactly
+};
+
+// ------------------------------------------------------------------------------------------
+// Ray
+// ------------------------------------------------------------------------------------------
+struct Ray {
+	double ox, oy, oz;
+	double dx, dy, dz;
+	double time;
+};
+
+struct Hit {
+	double t;
+	uint32_t ref;  // kind<<30 | index into spheres/quads; 0xffffffff = miss
+	double u, v;   // quad barycentrics (alpha, beta); spheres compute uv on demand
+};
+constexpr uint32_t kNoHit = 0xffffffffu;
+
+// Sphere::hit, sphere.rs:64-92.  `a` = |d|^2 is hoisted out by the caller (ray constant).
+// strict interval (surrounds, interval.rs:33-35).
+__device__ __forceinline__ bool hit_sphere(const DSphere& s, const double4* __restrict__ path, uint32_t index, const Ray& r, double a,
+                                           double tmin, double tmax, double& t_out) {
+	double cx = s.cx, cy = s.cy, cz = s.cz, rad = s.r;
+	if (rad < 0.0) {  // moving: center_start + time * center_path (sphere.rs:51-53)
+		double4 p = path[index];
+		cx = cx + r.time * p.x; cy = cy + r.time * p.y; cz = cz + r.time * p.z;
+		rad = -rad;
+	}
+	double ocx = cx - r.ox, ocy = cy - r.oy, ocz = cz - r.oz;
+	double h = r.dx * ocx + r.dy * ocy + r.dz * ocz;
+	double c = (ocx * ocx + ocy * ocy + ocz * ocz) - rad * rad;
+	double disc = h * h - a * c;
+	if (disc < 0.0) return false;
+	double sq = sqrt(disc);
+	double t = (h - sq) / a;
+	if (!(tmin < t && t < tmax)) {
+		t = (h + sq) / a;
+		if (!(tmin < t && t < tmax)) return false;
+	}
+	t_out = t;
+	return true;
+}
+
+// Quad::hit + Plane::hit, quad.rs:84-93 and plane.rs:20-32.  inclusive interval (contains).
+__device__ __forceinline__ bool hit_quad(const DQuad& q, const Ray& r, double tmin, double tmax, double& t_out, double& alpha, double& beta) {
+	double den = q.nx * r.dx + q.ny * r.dy + q.nz * r.dz;
+	if (fabs(den) < 1e-8) return false;
+	double t = (q.d - (q.nx * r.ox + q.ny * r.oy + q.nz * r.oz)) / den;
+	if (!(tmin <= t && t <= tmax)) return false;
+	double px = r.ox + r.dx * t, py = r.oy + r.dy * t, pz = r.oz + r.dz * t;
+	double al = (px * q.ax + py * q.ay + pz * q.az) - q.qa;
+	double be = (px * q.bx + py * q.by + pz * q.bz) - q.qb;
+	if (!(0.0 <= al && al <= 1.0) || !(0.0 <= be && be <= 1.0)) return false;
+	t_out = t; alpha = al; beta = be;
+	return true;
+}
+
+__device__ __forceinline__ DSphere load_sphere(const DSphere* __restrict__ p, uint32_t i) {
+	const double2* q = reinterpret_cast<const double2*>(p + i);
+	double2 a = __ldg(q), b = __ldg(q + 1);
+	return DSphere{a.x, a.y, b.x, b.y};
+}
+__device__ __forceinline__ DQuad load_quad(const DQuad* __restrict__ p, uint32_t i) {
+	const double2* q = reinterpret_cast<const double2*>(p + i);
+	double2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3), e = __ldg(q + 4), f = __ldg(q + 5);
+	return DQuad{a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y, e.x, e.y, f.x, f.y};
+}
+
+__device__ __forceinline__ float safe_rcp(float d) {
+	// 1/0 = inf in the reference (AABB.rs:64); a huge finite inverse orders the slabs identically without NaNs
+	float ad = fabsf(d);
+	return ad < 1e-30f ? copysignf(1e30f, d) : 1.0f / d;
+}
+
+// ------------------------------------------------------------------------------------------
+// Closest hit over the surface BVH: BVHNode::hit + AABB::hit + HittableList::hit collapsed into an
+// ordered while-while traversal with a per-thread stack.  Result equals the reference's
+// unordered recursion (BVH.rs:68-90) except on exact ties.
+// ------------------------------------------------------------------------------------------
+template <bool kCount>
+__device__ __forceinline__ Hit trace_closest(const DeviceScene& sc, const Ray& r, double tmin, double tmax, uint32_t* node_visits = nullptr) {
+	Hit best;
+	best.t = tmax; best.ref = kNoHit; best.u = 0.0; best.v = 0.0;
+	const float ox = (float)r.ox, oy = (float)r.oy, oz = (float)r.oz;
+	const float idx = safe_rcp((float)r.dx), idy = safe_rcp((float)r.dy), idz = safe_rcp((float)r.dz);
+	const double a = r.dx * r.dx + r.dy * r.dy + r.dz * r.dz;  // length_squared (sphere.rs:71)
+	float tmax32 = tmax >= 3.0e38 ? 3.4028235e38f : __double2float_ru(tmax);
+
+	int stack[kMaxStack];
+	int sp = 0;
+	stack[sp++] = kStackSentinel;
+	int node = sc.root;
+
+	while (node != kStackSentinel) {
+		while (node >= 0) {
+			const float4* np = reinterpret_cast<const float4*>(sc.nodes + node);
+			const float4 xy0 = __ldg(np), xy1 = __ldg(np + 1), z01 = __ldg(np + 2);
+			const int4 link = __ldg(reinterpret_cast<const int4*>(np + 3));
+			if (kCount) ++(*node_visits);
+			// child 0
+			float t0 = (xy0.x - ox) * idx, t1 = (xy0.y - ox) * idx;
+			float t2 = (xy0.z - oy) * idy, t3 = (xy0.w - oy) * idy;
+			float t4 = (z01.x - oz) * idz, t5 = (z01.y - oz) * idz;
+			float en0 = fmaxf(fmaxf(fminf(t0, t1), fminf(t2, t3)), fmaxf(fminf(t4, t5), 0.0f));
+			float ex0 = fminf(fminf(fmaxf(t0, t1), fmaxf(t2, t3)), fminf(fmaxf(t4, t5), tmax32));
+			// child 1
+			t0 = (xy1.x - ox) * idx; t1 = (xy1.y - ox) * idx;
+			t2 = (xy1.z - oy) * idy; t3 = (xy1.w - oy) * idy;
+			t4 = (z01.z - oz) * idz; t5 = (z01.w - oz) * idz;
+			float en1 = fmaxf(fmaxf(fminf(t0, t1), fminf(t2, t3)), fmaxf(fminf(t4, t5), 0.0f));
+			float ex1 = fminf(fminf(fmaxf(t0, t1), fmaxf(t2, t3)), fminf(fmaxf(t4, t5), tmax32));
+			const bool h0 = en0 <= ex0, h1 = en1 <= ex1;
+			if (!h0 && !h1) { node = stack[--sp]; }
+			else {
+				int near = link.x, far = link.y;
+				if (h0 && h1) {
+					if (en1 < en0) { int tmp = near; near = far; far = tmp; }
+					stack[sp++] = far;
+					node = near;
+				} else node = h0 ? near : far;
+			}
+		}
+		if (node == kStackSentinel) break;
+		// leaf
+		{
+			const uint32_t code = (uint32_t)(-1 - node);
+			const uint32_t first = code >> 4, count = code & 15u;
+			for (uint32_t k = 0; k < count; ++k) {
+				const uint32_t ref = __ldg(sc.refs + first + k);
+				const uint32_t index = ref & kRefIndexMask;
+				if ((ref >> kRefKindShift) == 0u) {
+					const DSphere s = load_sphere(sc.spheres, index);
+					double t;
+					if (hit_sphere(s, sc.sph_path, index, r, a, tmin, best.t, t)) { best.t = t; best.ref = ref; }
+				} else {
+					const DQuad q = load_quad(sc.quads, index);
+					double t, al, be;
+					if (hit_quad(q, r, tmin, best.t, t, al, be)) {
+						// exact tie between two quads: the one the reference visits later wins (t <= closest, plane.rs:27)
+						bool accept = true;
+						if (t == best.t && best.ref != kNoHit && (best.ref >> kRefKindShift) == 1u)
+							accept = __ldg(sc.quad_order + index) > __ldg(sc.quad_order + (best.ref & kRefIndexMask));
+						if (accept) { best.t = t; best.ref = ref; best.u = al; best.v = be; }
+					}
+				}
+			}
+			if (best.ref != kNoHit) tmax32 = __double2float_ru(best.t);
+			node = stack[--sp];
+		}
+	}
+	return best;
+}
+
+}  // namespace gs

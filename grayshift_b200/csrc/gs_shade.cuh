@@ -1,0 +1,372 @@
+// grayshift_b200/csrc/gs_shade.cuh -- ray generation, media, materials, textures, environment map and
+// the iterative form of Camera::ray_color for the render kernels.  fp32 shading on f64 hit points.
+// Every function cites the reference file:line (relative to /root/reference) whose behaviour it keeps,
+// quirks included.
+#pragma once
+#include "gs_device.cuh"
+
+namespace gs {
+
+struct f3 { float x, y, z; };
+__device__ __forceinline__ f3 mk3(float x, float y, float z) { f3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ f3 operator+(f3 a, f3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ f3 operator-(f3 a, f3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ f3 operator-(f3 a) { return mk3(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ f3 operator*(f3 a, float s) { return mk3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ f3 operator*(f3 a, f3 b) { return mk3(a.x * b.x, a.y * b.y, a.z * b.z); }
+__device__ __forceinline__ float dot(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ f3 cross(f3 a, f3 b) { return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+__device__ __forceinline__ f3 unit(f3 a) { float inv = rsqrtf(dot(a, a)); return a * inv; }
+
+constexpr float kPi = 3.14159265358979323846f;
+
+// ---- random helpers, util.rs:18-60 ---------------------------------------------------------------
+__device__ __forceinline__ f3 random_unit_vector(PathRng& rng) {  // util.rs:18-29 (3 draws per rejection round)
+	for (;;) {
+		float x = rng.next_f32() * 2.0f - 1.0f;
+		float y = rng.next_f32() * 2.0f - 1.0f;
+		float z = rng.next_f32() * 2.0f - 1.0f;
+		float l2 = x * x + y * y + z * z;
+		if (l2 < 1.0f) { float inv = rsqrtf(l2); return mk3(x * inv, y * inv, z * inv); }
+	}
+}
+__device__ __forceinline__ f3 random_cosine_direction(PathRng& rng) {  // util.rs:48-60: NOT cosine weighted (Q1): r2^(1/4)
+	float r1 = rng.next_f32();
+	float r2 = rng.next_f32();
+	float s, c;
+	sincospif(2.0f * r1, &s, &c);
+	float q = sqrtf(sqrtf(r2));
+	return mk3(c * q, s * q, sqrtf(1.0f - r2));
+}
+
+// ---- Camera::get_ray, camera.rs:204-226 (f64, same draws as the oracle) --------------------------
+__device__ __forceinline__ Ray get_ray(const DCamera& cam, int i, int j, PathRng& rng) {
+	double offset_x = rng.next_f64() - 0.5;
+	double offset_y = rng.next_f64() - 0.5;
+	double fi = (double)i + offset_x, fj = (double)j + offset_y;
+	double psx = cam.pixel00[0] + fi * cam.du[0] + fj * cam.dv[0];
+	double psy = cam.pixel00[1] + fi * cam.du[1] + fj * cam.dv[1];
+	double psz = cam.pixel00[2] + fi * cam.du[2] + fj * cam.dv[2];
+	Ray r;
+	r.ox = cam.center[0]; r.oy = cam.center[1]; r.oz = cam.center[2];
+	if (cam.defocus_angle > 0.0) {  // defocus_disk_sample: rejection in the unit disk, util.rs:36-46
+		double vx, vy;
+		for (;;) {
+			vx = rng.next_f64() * 2.0 + -1.0;
+			vy = rng.next_f64() * 2.0 + -1.0;
+			if (vx * vx + vy * vy < 1.0) break;
+		}
+		r.ox = cam.center[0] + vx * cam.disk_u[0] + vy * cam.disk_v[0];
+		r.oy = cam.center[1] + vx * cam.disk_u[1] + vy * cam.disk_v[1];
+		r.oz = cam.center[2] + vx * cam.disk_u[2] + vy * cam.disk_v[2];
+	}
+	r.dx = psx - r.ox; r.dy = psy - r.oy; r.dz = psz - r.oz;  // not normalised (Q6)
+	r.time = rng.next_f64();                                  // always drawn (Q7)
+	return r;
+}
+
+// ---- HDRI::sample, camera.rs:257-270 ----------------------------------------------------------------
+__device__ __forceinline__ f3 background(const DeviceScene& sc, const DCamera& cam, f3 d, uint32_t& tex_fetches) {
+	if (cam.bg_kind == 0) return mk3(cam.bg[0], cam.bg[1], cam.bg[2]);
+	f3 r = mk3(d.x * cam.rot[0] + d.y * cam.rot[1] + d.z * cam.rot[2],
+	           d.x * cam.rot[3] + d.y * cam.rot[4] + d.z * cam.rot[5],
+	           d.x * cam.rot[6] + d.y * cam.rot[7] + d.z * cam.rot[8]);
+	r = unit(r);
+	float theta = atan2f(r.y, r.x);
+	float phi = asinf(fminf(fmaxf(r.z, -1.0f), 1.0f));
+	float u = 0.5f + theta * (0.5f / kPi);
+	float v = 0.5f - phi * (1.0f / kPi);
+	const DImage im = sc.images[cam.hdri_image];
+	int x = (int)fmaxf(u * (float)im.w, 0.0f) % im.w;  // `as usize` saturates negatives to 0, then % W (camera.rs:265-266)
+	int y = (int)fmaxf(v * (float)im.h, 0.0f) % im.h;
+	float4 c = __ldg(reinterpret_cast<const float4*>(im.texels) + (size_t)y * im.w + x);
+	++tex_fetches;
+	return mk3(c.x, c.y, c.z);
+}
+
+// ---- Perlin (noise 0.9.0, restated; see oracle.cpp) on a shared-memory permutation table ------------
+__device__ __forceinline__ float perlin_grad(uint32_t h, float x, float y, float z) {
+	switch (h & 15u) {
+		case 0: case 12: return x + y;
+		case 1: case 14: return -x + y;
+		case 2: return x - y;
+		case 3: return -x - y;
+		case 4: return x + z;
+		case 5: return -x + z;
+		case 6: return x - z;
+		case 7: return -x - z;
+		case 8: return y + z;
+		case 9: case 13: return -y + z;
+		case 10: return y - z;
+		default: return -y - z;
+	}
+}
+__device__ __forceinline__ float perlin_get(const uint8_t* __restrict__ perm, double px, double py, double pz) {
+	double fx = floor(px), fy = floor(py), fz = floor(pz);
+	int cx = (int)(long long)fx, cy = (int)(long long)fy, cz = (int)(long long)fz;
+	float dx = (float)(px - fx), dy = (float)(py - fy), dz = (float)(pz - fz);
+	uint32_t hx0 = perm[cx & 255], hx1 = perm[(cx + 1) & 255];
+	uint32_t y0 = (uint32_t)(cy & 255), y1 = (uint32_t)((cy + 1) & 255), z0 = (uint32_t)(cz & 255), z1 = (uint32_t)((cz + 1) & 255);
+	uint32_t h00 = perm[hx0 ^ y0], h10 = perm[hx1 ^ y0], h01 = perm[hx0 ^ y1], h11 = perm[hx1 ^ y1];
+	float g000 = perlin_grad(perm[h00 ^ z0], dx, dy, dz), g100 = perlin_grad(perm[h10 ^ z0], dx - 1.f, dy, dz);
+	float g010 = perlin_grad(perm[h01 ^ z0], dx, dy - 1.f, dz), g110 = perlin_grad(perm[h11 ^ z0], dx - 1.f, dy - 1.f, dz);
+	float g001 = perlin_grad(perm[h00 ^ z1], dx, dy, dz - 1.f), g101 = perlin_grad(perm[h10 ^ z1], dx - 1.f, dy, dz - 1.f);
+	float g011 = perlin_grad(perm[h01 ^ z1], dx, dy - 1.f, dz - 1.f), g111 = perlin_grad(perm[h11 ^ z1], dx - 1.f, dy - 1.f, dz - 1.f);
+	float a = dx * dx * dx * (dx * (dx * 6.f - 15.f) + 10.f);
+	float b = dy * dy * dy * (dy * (dy * 6.f - 15.f) + 10.f);
+	float c = dz * dz * dz * (dz * (dz * 6.f - 15.f) + 10.f);
+	float k1 = g100 - g000, k2 = g010 - g000, k3 = g001 - g000;
+	float k4 = g000 + g110 - g100 - g010, k5 = g000 + g101 - g100 - g001, k6 = g000 + g011 - g010 - g001;
+	float k7 = g100 + g010 + g001 + g111 - g000 - g110 - g101 - g011;
+	float v = g000 + k1 * a + k2 * b + k3 * c + k4 * a * b + k5 * a * c + k6 * b * c + k7 * a * b * c;
+	v *= 1.1547005383792515f;
+	return fminf(fmaxf(v, -1.0f), 1.0f);
+}
+
+// ---- Texture::value_at, texture.rs:27-30, 57-70, 84-94, 107-130 --------------------------------------
+struct Surface {
+	double px, py, pz;  // hit position (f64: it is the next ray's origin)
+	f3 n;               // shading normal, flipped against the ray (hittable.rs:35-36)
+	f3 n_out;           // outward (unflipped) normal; spheres derive (u,v) from it
+	float u, v;
+	bool front, is_sphere;
+	int material;
+};
+
+__device__ __forceinline__ f3 texture_value(const DeviceScene& sc, const uint8_t* __restrict__ perm, int tex, const Surface& s, uint32_t& tex_fetches) {
+#pragma unroll 1
+	for (int depth = 0; depth < 16; ++depth) {
+		const DTexture* tp = sc.textures + tex;
+		const int4 head = __ldg(reinterpret_cast<const int4*>(tp));  // kind, a, b, scale(float bits)
+		if (head.x == 0) {  // SolidColorTexture
+			const float4 col = __ldg(reinterpret_cast<const float4*>(tp) + 1);
+			return mk3(col.x, col.y, col.z);
+		}
+		if (head.x == 1) {  // CheckeredTexture: floor(scale_inv * p) as i32, (x+y+z) % 2 == 0 (texture.rs:58-63)
+			const double2 sd = __ldg(reinterpret_cast<const double2*>(tp) + 2);  // scale_inv, scale
+			int xi = __double2int_rd(sd.x * s.px), yi = __double2int_rd(sd.x * s.py), zi = __double2int_rd(sd.x * s.pz);
+			int sum = xi + yi + zi;
+			tex = (sum % 2 == 0) ? head.y : head.z;
+			continue;
+		}
+		if (head.x == 2) {  // ImageTexture: nearest texel, v flipped, /255 (texture.rs:84-94); Q13 clamps the index
+			float u = s.u, v = s.v;
+			if (s.is_sphere) {  // sphere_uv, sphere.rs:55-60
+				float theta = acosf(fminf(fmaxf(-s.n_out.y, -1.0f), 1.0f));
+				float phi = atan2f(-s.n_out.z, s.n_out.x) + kPi;
+				u = phi * (0.5f / kPi); v = theta * (1.0f / kPi);
+			}
+			const DImage im = sc.images[head.y];
+			float uc = fminf(fmaxf(u, 0.0f), 1.0f), vc = 1.0f - fminf(fmaxf(v, 0.0f), 1.0f);
+			int i = min((int)(uc * (float)im.w), im.w - 1), j = min((int)(vc * (float)im.h), im.h - 1);
+			uchar4 px = __ldg(reinterpret_cast<const uchar4*>(im.texels) + (size_t)j * im.w + i);
+			++tex_fetches;
+			return mk3((float)px.x * (1.0f / 255.0f), (float)px.y * (1.0f / 255.0f), (float)px.z * (1.0f / 255.0f));
+		}
+		{  // NoiseTexture: 0.5 * (1 + sin(scale*z + 10*turb(p, 7))) (texture.rs:107-130)
+			const double2 sd = __ldg(reinterpret_cast<const double2*>(tp) + 2);
+			float accum = 0.0f, weight = 1.0f;
+			double sx = s.px, sy = s.py, sz = s.pz;
+#pragma unroll 1
+			for (int i = 0; i < 7; ++i) {
+				accum += weight * perlin_get(perm, sx, sy, sz);
+				weight *= 0.5f;
+				sx *= 2.0; sy *= 2.0; sz *= 2.0;
+			}
+			float g = 0.5f * (1.0f + sinf((float)(sd.y * s.pz) + 10.0f * fabsf(accum)));
+			return mk3(g, g, g);
+		}
+	}
+	return mk3(0.f, 0.f, 0.f);
+}
+
+// ---- Material::emitted / scatter, material.rs:45-68, 87-102, 122-148, 165-169, 186-196 ------------
+// returns false when the path ends here (no scatter); emission is added to `emit`.
+__device__ __forceinline__ bool shade(const DeviceScene& sc, const uint8_t* __restrict__ perm, const Surface& s, f3 d_in, PathRng& rng,
+                                      f3& emit, f3& atten, f3& d_out, uint32_t& tex_fetches) {
+	const DMaterial* mp = sc.materials + s.material;
+	const int4 m0 = __ldg(reinterpret_cast<const int4*>(mp));        // kind, tex, albedo.r, albedo.g
+	const float4 m1 = __ldg(reinterpret_cast<const float4*>(mp) + 1);  // albedo.b, param
+	emit = mk3(0.f, 0.f, 0.f);
+	switch (m0.x) {
+		case 0: {  // Lambertian
+			atten = texture_value(sc, perm, m0.y, s, tex_fetches);
+			// OrthonormalBasis::new, ONB.rs:10-23
+			f3 w = unit(s.n);
+			f3 a = fabsf(w.x) > 0.9f ? mk3(0.f, 1.f, 0.f) : mk3(1.f, 0.f, 0.f);
+			f3 v = unit(cross(w, a));
+			f3 u = cross(w, v);
+			f3 l = random_cosine_direction(rng);
+			d_out = unit(u * l.x + v * l.y + w * l.z);
+			return true;
+		}
+		case 1: {  // Metal: unit(reflect) + fuzz * random_unit_vector, drawn even when fuzz == 0 (Q7)
+			f3 refl = d_in - s.n * (2.0f * dot(d_in, s.n));
+			f3 rv = random_unit_vector(rng);
+			d_out = unit(refl) + rv * m1.y;
+			atten = mk3(__int_as_float(m0.z), __int_as_float(m0.w), m1.x);
+			return dot(d_out, s.n) > 0.0f;
+		}
+		case 2: {  // Dielectric
+			float ir = m1.y;
+			float ri = s.front ? 1.0f / ir : ir;
+			f3 ud = unit(d_in);
+			float cos_theta = fminf(-dot(ud, s.n), 1.0f);
+			float sin_theta = sqrtf(fmaxf(1.0f - cos_theta * cos_theta, 0.0f));
+			bool cannot_refract = ri * sin_theta > 1.0f;
+			float r0 = (1.0f - ri) / (1.0f + ri);
+			r0 = r0 * r0;
+			float m = 1.0f - cos_theta;
+			float reflectance = r0 + (1.0f - r0) * (m * m * m * m * m);
+			bool fresnel = reflectance > rng.next_f32();  // always drawn (Q7)
+			if (cannot_refract || fresnel) d_out = ud - s.n * (2.0f * dot(ud, s.n));
+			else {  // Vec3::refract, vec3.rs:57-62
+				float ct = fminf(dot(s.n, -ud), 1.0f);
+				f3 perp = (ud + s.n * ct) * ri;
+				f3 par = s.n * (-sqrtf(fabsf(1.0f - dot(perp, perp))));
+				d_out = perp + par;
+			}
+			atten = mk3(1.f, 1.f, 1.f);
+			return true;
+		}
+		case 3: {  // DiffuseLight: two-sided, never scatters (Q8)
+			emit = texture_value(sc, perm, m0.y, s, tex_fetches);
+			return false;
+		}
+		default: {  // Isotropic
+			atten = texture_value(sc, perm, m0.y, s, tex_fetches);
+			d_out = random_unit_vector(rng);
+			return true;
+		}
+	}
+}
+
+// ---- ConstantMedium::hit, volume.rs:32-63, evaluated per ray before the surface traversal ---------
+// Statistically identical to the reference's in-traversal evaluation: the free-flight draw is
+// independent of everything else, so testing the medium first and clipping the surface search at
+// its candidate t gives the same closest-event distribution.
+__device__ __forceinline__ bool boundary_closest(const DeviceScene& sc, const DMedium& m, const Ray& r, double a, double lo, double hi,
+                                                 bool strict_only, double& t_out) {
+	bool found = false;
+	double best = hi;
+	for (int k = 0; k < m.sph_count; ++k) {
+		DSphere s = load_sphere(sc.bnd_spheres, m.sph_first + k);
+		double t;
+		if (hit_sphere(s, sc.bnd_sph_path, m.sph_first + k, r, a, lo, best, t)) { best = t; found = true; }
+	}
+	for (int k = 0; k < m.quad_count; ++k) {
+		DQuad q = load_quad(sc.bnd_quads, m.quad_first + k);
+		double t, al, be;
+		if (hit_quad(q, r, lo, best, t, al, be)) { best = t; found = true; }
+	}
+	t_out = best;
+	return found;
+}
+
+__device__ __forceinline__ bool medium_event(const DeviceScene& sc, const DMedium& m, const Ray& r, double a, double tmin, double tmax,
+                                             float u01, double& t_out) {
+	double t1, t2;
+	if (!boundary_closest(sc, m, r, a, -1.7976931348623157e308, 1.7976931348623157e308, false, t1)) return false;  // Interval::UNIVERSE
+	if (!boundary_closest(sc, m, r, a, t1 + 0.0001, 1.7976931348623157e308, false, t2)) return false;
+	if (t1 < tmin) t1 = tmin;
+	if (t2 > tmax) t2 = tmax;
+	if (t1 >= t2) return false;
+	if (t1 < 0.0) t1 = 0.0;
+	double ray_len = sqrt(a);
+	double dist_inside = (t2 - t1) * ray_len;
+	double hit_dist = m.neg_inv_density * (double)logf(u01);
+	if (hit_dist > dist_inside) return false;
+	t_out = t1 + hit_dist / ray_len;
+	return true;
+}
+
+// ---- Camera::ray_color, camera.rs:174-202, iterative: L = sum_k (prod_{j<k} att_j) E_k (+ background) ---
+struct PathCounters { uint32_t rays, tex_fetches, node_visits; };
+
+struct PathState {
+	Ray ray;
+	f3 L, T;
+	PathRng rng;
+	unsigned bounce;
+	uint32_t pixel;
+};
+
+__device__ __forceinline__ void path_begin(PathState& st, const DCamera& cam, uint64_t seed, uint32_t pixel, uint32_t sample) {
+	st.rng.start(seed, pixel, sample);
+	st.pixel = pixel;
+	st.ray = get_ray(cam, (int)(pixel % (uint32_t)cam.width), (int)(pixel / (uint32_t)cam.width), st.rng);
+	st.L = mk3(0.f, 0.f, 0.f);
+	st.T = mk3(1.f, 1.f, 1.f);
+	st.bounce = 0;
+}
+
+// One world.hit + emitted + scatter (one level of the reference's recursion).  Returns true when the
+// path is finished (miss, absorbed, light, or depth exhausted); st.L then holds the sample colour.
+template <bool kCount>
+__device__ __forceinline__ bool path_step(const DeviceScene& sc, const DCamera& cam, const uint8_t* __restrict__ perm, PathState& st,
+                                          PathCounters& pc) {
+	if (st.bounce >= cam.max_depth) return true;  // `if depth <= 0 { return ZERO }`, camera.rs:175
+	Ray& ray = st.ray;
+	++pc.rays;
+	double tmax = 1.7976931348623157e308;  // Interval::new(0.001, f64::MAX), camera.rs:177
+	int medium_hit = -1;
+	if (sc.n_media > 0) {
+		const double a = ray.dx * ray.dx + ray.dy * ray.dy + ray.dz * ray.dz;
+		// media stream: counter word 3 = 1, block = bounce * 64 + group, 4 media per block
+		uint4 blk = make_uint4(0u, 0u, 0u, 0u);
+		for (int mi = 0; mi < sc.n_media; ++mi) {
+			if ((mi & 3) == 0) blk = philox4x32_10(st.rng.pixel, st.rng.sample, st.bounce * 64u + (uint32_t)(mi >> 2), 1u, st.rng.k0, st.rng.k1);
+			uint32_t w = (mi & 3) == 0 ? blk.x : ((mi & 3) == 1 ? blk.y : ((mi & 3) == 2 ? blk.z : blk.w));
+			float u01 = (float)(w >> 8) * (1.0f / 16777216.0f);
+			double tm;
+			if (medium_event(sc, sc.media[mi], ray, a, 0.001, tmax, u01, tm)) { tmax = tm; medium_hit = mi; }
+		}
+	}
+	Hit h = trace_closest<kCount>(sc, ray, 0.001, tmax, &pc.node_visits);
+	f3 d_in = mk3((float)ray.dx, (float)ray.dy, (float)ray.dz);
+	if (h.ref == kNoHit && medium_hit < 0) {  // sample_background, camera.rs:228-233
+		f3 bg = background(sc, cam, d_in, pc.tex_fetches);
+		st.L = st.L + st.T * bg;
+		return true;
+	}
+	Surface s;
+	f3 n_out;
+	if (h.ref != kNoHit) {
+		const uint32_t index = h.ref & kRefIndexMask;
+		s.px = ray.ox + ray.dx * h.t; s.py = ray.oy + ray.dy * h.t; s.pz = ray.oz + ray.dz * h.t;  // ray.at(t)
+		if ((h.ref >> kRefKindShift) == 0u) {
+			DSphere sp = load_sphere(sc.spheres, index);
+			double cx = sp.cx, cy = sp.cy, cz = sp.cz, rad = sp.r;
+			if (rad < 0.0) { double4 p = sc.sph_path[index]; cx += ray.time * p.x; cy += ray.time * p.y; cz += ray.time * p.z; rad = -rad; }
+			double inv_r = 1.0 / rad;
+			n_out = mk3((float)((s.px - cx) * inv_r), (float)((s.py - cy) * inv_r), (float)((s.pz - cz) * inv_r));  // sphere.rs:91
+			s.is_sphere = true; s.u = 0.f; s.v = 0.f;
+			s.material = __ldg(sc.sph_aux + index).x;
+		} else {
+			const double2* qp = reinterpret_cast<const double2*>(sc.quads + index);
+			double2 n01 = __ldg(qp), n23 = __ldg(qp + 1);
+			n_out = mk3((float)n01.x, (float)n01.y, (float)n23.x);
+			s.is_sphere = false; s.u = (float)h.u; s.v = (float)h.v;
+			s.material = __ldg(sc.quad_aux + index).x;
+		}
+	} else {  // medium event: normal (1,0,0), u = v = 0, phase function as the material (volume.rs:54-62, Q10)
+		s.px = ray.ox + ray.dx * tmax; s.py = ray.oy + ray.dy * tmax; s.pz = ray.oz + ray.dz * tmax;
+		n_out = mk3(1.f, 0.f, 0.f);
+		s.is_sphere = false; s.u = 0.f; s.v = 0.f;
+		s.material = sc.media[medium_hit].phase_mat;
+	}
+	s.front = dot(d_in, n_out) < 0.0f;  // HitRecord::new, hittable.rs:35-36
+	s.n = s.front ? n_out : -n_out;
+	s.n_out = n_out;
+	f3 emit, atten, d_out;
+	bool scattered = shade(sc, perm, s, d_in, st.rng, emit, atten, d_out, pc.tex_fetches);
+	st.L = st.L + st.T * emit;
+	if (!scattered) return true;
+	st.T = st.T * atten;
+	ray.ox = s.px; ray.oy = s.py; ray.oz = s.pz;
+	ray.dx = (double)d_out.x; ray.dy = (double)d_out.y; ray.dz = (double)d_out.z;
+	++st.bounce;
+	return false;
+}
+
+}  // namespace gs

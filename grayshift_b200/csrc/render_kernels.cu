@@ -1,0 +1,248 @@
+// grayshift_b200/csrc/render_kernels.cu -- the render kernels for sm_100a.
+//
+// render_fixed_kernel: persistent megakernel for fixed sample counts (tolerance == 0).  Replaces the
+//   rayon per-pixel loop + Camera::sample + ray_color (camera.rs:100-202).  One warp = 32 independent
+//   paths; a lane whose path ends takes the next (pixel, sample) item at the top of the next
+//   iteration (path regeneration), so the warp stays full until the whole image is exhausted.
+//   Work items are handed out in chunks through one global 64-bit atomic per warp per chunk.
+//   Each lane keeps (sum r, sum g, sum b, n) for its current pixel in registers and flushes with one
+//   128-bit vector reduction (red.global.add.v4.f32) when its pixel changes.
+// render_adaptive_kernel: the reference's adaptive sampler (camera.rs:125-171) with exact batch /
+//   stop-test semantics (Q3-Q5): one warp per pixel, a batch's samples spread over the lanes.
+// Grids are sized to SM count x resident CTAs (persistent), never to the image.
+#include "gs_internal.h"
+#include "gs_shade.cuh"
+
+namespace gs {
+
+constexpr int kBlock = 128;
+constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ void red_add_v4(float4* addr, float a, float b, float c, float d) {
+	asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__device__ __forceinline__ void load_perm(uint8_t* s_perm, const uint8_t* g_perm) {
+	for (int i = threadIdx.x; i < 256; i += blockDim.x) s_perm[i] = g_perm ? g_perm[i] : (uint8_t)i;
+	__syncthreads();
+}
+
+__device__ __forceinline__ void flush_stats(unsigned long long* stats, const PathCounters& pc, unsigned paths) {
+	unsigned r = pc.rays, t = pc.tex_fetches, n = pc.node_visits, p = paths;
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) {
+		r += __shfl_xor_sync(kFull, r, o); t += __shfl_xor_sync(kFull, t, o);
+		n += __shfl_xor_sync(kFull, n, o); p += __shfl_xor_sync(kFull, p, o);
+	}
+	// per-thread counters are 32-bit; one warp handles far fewer than 2^32 rays per launch
+	if ((threadIdx.x & 31) == 0) {
+		atomicAdd(stats + 0, (unsigned long long)r); atomicAdd(stats + 1, (unsigned long long)p);
+		atomicAdd(stats + 2, (unsigned long long)t); atomicAdd(stats + 3, (unsigned long long)n);
+	}
+}
+
+template <bool kCount>
+__global__ void __launch_bounds__(kBlock) render_fixed_kernel(const __grid_constant__ RenderParams P) {
+	__shared__ uint8_t s_perm[256];
+	load_perm(s_perm, P.sc.perlin_perm);
+	const unsigned lane = threadIdx.x & 31u;
+	const unsigned lt_mask = (1u << lane) - 1u;
+	PathCounters pc = {0u, 0u, 0u};
+	unsigned paths = 0;
+	PathState st;
+	bool alive = false;
+	float ar = 0.f, ag = 0.f, ab = 0.f, an = 0.f;
+	uint32_t cur_pixel = 0xffffffffu;
+	unsigned long long warp_next = 0, warp_end = 0;
+	bool exhausted = false;
+
+	for (;;) {
+		const unsigned dead = __ballot_sync(kFull, !alive);
+		if (dead) {
+			if (warp_next >= warp_end && !exhausted) {
+				unsigned long long base = 0;
+				if (lane == 0) base = atomicAdd(P.work_counter, (unsigned long long)P.chunk);
+				base = __shfl_sync(kFull, base, 0);
+				if (base >= P.total_items) exhausted = true;
+				else { warp_next = base; warp_end = min(base + (unsigned long long)P.chunk, P.total_items); }
+			}
+			const unsigned long long avail = warp_end - warp_next;
+			if (!alive) {
+				const unsigned rank = __popc(dead & lt_mask);
+				if (rank < avail) {
+					const unsigned long long item = warp_next + rank;
+					const uint32_t pixel = (uint32_t)(item / P.sample_count);
+					const uint32_t sample = (uint32_t)(item % P.sample_count) + P.sample_begin;
+					path_begin(st, P.cam, P.seed, pixel, sample);
+					alive = true;
+					++paths;
+				}
+			}
+			const unsigned long long need = (unsigned long long)__popc(dead);
+			warp_next += need < avail ? need : avail;
+		}
+		if (!__any_sync(kFull, alive)) {
+			if (exhausted) break;
+			continue;
+		}
+		if (alive) {
+			if (path_step<kCount>(P.sc, P.cam, s_perm, st, pc)) {
+				if (st.pixel != cur_pixel) {
+					if (cur_pixel != 0xffffffffu) red_add_v4(P.accum + cur_pixel, ar, ag, ab, an);
+					cur_pixel = st.pixel; ar = ag = ab = an = 0.f;
+				}
+				ar += st.L.x; ag += st.L.y; ab += st.L.z; an += 1.f;  // pixel_color += sample_color, camera.rs:141
+				alive = false;
+			}
+		}
+	}
+	if (cur_pixel != 0xffffffffu) red_add_v4(P.accum + cur_pixel, ar, ag, ab, an);
+	flush_stats(P.stats, pc, paths);
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+	return v;
+}
+
+__global__ void __launch_bounds__(kBlock) render_adaptive_kernel(const __grid_constant__ AdaptiveParams P) {
+	__shared__ uint8_t s_perm[256];
+	load_perm(s_perm, P.sc.perlin_perm);
+	const unsigned lane = threadIdx.x & 31u;
+	const unsigned lt_mask = (1u << lane) - 1u;
+	PathCounters pc = {0u, 0u, 0u};
+	unsigned paths = 0;
+	for (;;) {
+		unsigned long long k = 0;
+		if (lane == 0) k = atomicAdd(P.work_counter, 1ull);
+		k = __shfl_sync(kFull, k, 0);
+		if (k >= P.n_pixels) break;
+		const uint32_t pixel = P.pixel_begin + (uint32_t)k * P.pixel_stride;
+		double sum = 0.0, sq_sum = 0.0, cr = 0.0, cg = 0.0, cb = 0.0;  // this lane's share of camera.rs:131-133
+		double sample_count = 0.0;
+		unsigned next = 0;
+		for (;;) {
+			sample_count += (double)P.batch_size;  // camera.rs:137
+			const unsigned end = next + P.batch_size;
+			PathState st;
+			bool alive = false;
+			for (;;) {  // one batch, samples spread over the lanes with regeneration inside the batch
+				const unsigned dead = __ballot_sync(kFull, !alive);
+				if (dead) {
+					const unsigned avail = end - next;
+					if (!alive) {
+						const unsigned rank = __popc(dead & lt_mask);
+						if (rank < avail) { path_begin(st, P.cam, P.seed, pixel, next + rank); alive = true; ++paths; }
+					}
+					const unsigned need = __popc(dead);
+					next += need < avail ? need : avail;
+				}
+				if (!__any_sync(kFull, alive)) break;
+				if (alive && path_step<false>(P.sc, P.cam, s_perm, st, pc)) {
+					cr += (double)st.L.x; cg += (double)st.L.y; cb += (double)st.L.z;
+					const double lum = 0.299 * (double)st.L.x + 0.587 * (double)st.L.y + 0.144 * (double)st.L.z;  // color.rs:31-33
+					sum += lum; sq_sum += lum * lum;
+					alive = false;
+				}
+			}
+			const double tsum = warp_sum(sum), tsq = warp_sum(sq_sum);
+			const double mean = tsum / sample_count;  // camera.rs:150-158
+			const double variance_sq = 1.0 / (sample_count - 1.0) * (tsq - tsum * tsum / sample_count);
+			const double convergence_sq = P.confidence_sq * variance_sq / sample_count;
+			if (convergence_sq < mean * mean * P.tolerance_sq) break;
+			const unsigned sc_u32 = sample_count >= 4294967295.0 ? 4294967295u : (unsigned)sample_count;
+			if (sc_u32 > P.max_samples) break;  // camera.rs:162-164
+		}
+		const double tr = warp_sum(cr), tg = warp_sum(cg), tb = warp_sum(cb);
+		if (lane == 0) P.accum[pixel] = make_float4((float)tr, (float)tg, (float)tb, (float)sample_count);
+	}
+	flush_stats(P.stats, pc, paths);
+}
+
+// pixel_color /= sample_count (camera.rs:167)
+__global__ void resolve_kernel(const float4* __restrict__ accum, int n_pixels, float* __restrict__ out_rgb, unsigned* __restrict__ out_counts) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_pixels) return;
+	float4 a = accum[i];
+	float inv = a.w > 0.f ? 1.0f / a.w : 0.f;
+	out_rgb[i * 3 + 0] = a.x * inv; out_rgb[i * 3 + 1] = a.y * inv; out_rgb[i * 3 + 2] = a.z * inv;
+	if (out_counts) out_counts[i] = (unsigned)a.w;
+}
+
+__global__ void camera_rays_kernel(const __grid_constant__ DCamera cam, unsigned long long seed, unsigned sample, int pixel_begin, int pixel_end,
+                                   double* __restrict__ rays_out) {
+	int n = pixel_begin + blockIdx.x * blockDim.x + threadIdx.x;
+	if (n >= pixel_end) return;
+	PathRng rng;
+	rng.start(seed, (uint32_t)n, sample);
+	Ray r = get_ray(cam, n % cam.width, n / cam.width, rng);
+	double* o = rays_out + (size_t)(n - pixel_begin) * 7;
+	o[0] = r.ox; o[1] = r.oy; o[2] = r.oz; o[3] = r.dx; o[4] = r.dy; o[5] = r.dz; o[6] = r.time;
+}
+
+__global__ void __launch_bounds__(kBlock) path_radiance_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ DCamera cam,
+                                                               unsigned long long seed, const unsigned* __restrict__ pixel,
+                                                               const unsigned* __restrict__ sample, size_t n, float* __restrict__ out_rgb) {
+	__shared__ uint8_t s_perm[256];
+	load_perm(s_perm, sc.perlin_perm);
+	size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= n) return;
+	PathCounters pc = {0u, 0u, 0u};
+	PathState st;
+	path_begin(st, cam, seed, pixel[k], sample[k]);
+	while (!path_step<false>(sc, cam, s_perm, st, pc)) {}
+	out_rgb[k * 3 + 0] = st.L.x; out_rgb[k * 3 + 1] = st.L.y; out_rgb[k * 3 + 2] = st.L.z;
+}
+
+// ---- launch wrappers ------------------------------------------------------------------------------
+int render_fixed_blocks_per_sm(bool count_nodes) {
+	int n = 0;
+	if (count_nodes) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, render_fixed_kernel<true>, kBlock, 0);
+	else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, render_fixed_kernel<false>, kBlock, 0);
+	return n > 0 ? n : 1;
+}
+
+cudaError_t launch_render_fixed(const RenderParams& p, int sm_count, bool count_nodes, cudaStream_t stream) {
+	const int per_sm = render_fixed_blocks_per_sm(count_nodes);
+	unsigned long long warps_needed = (p.total_items + 31ull) / 32ull;
+	unsigned long long blocks_needed = (warps_needed + (kBlock / 32) - 1) / (kBlock / 32);
+	unsigned long long grid = (unsigned long long)sm_count * per_sm;  // persistent: SMs x resident CTAs
+	if (blocks_needed < grid) grid = blocks_needed ? blocks_needed : 1;
+	if (count_nodes) render_fixed_kernel<true><<<(unsigned)grid, kBlock, 0, stream>>>(p);
+	else render_fixed_kernel<false><<<(unsigned)grid, kBlock, 0, stream>>>(p);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_render_adaptive(const AdaptiveParams& p, int sm_count, cudaStream_t stream) {
+	int per_sm = 0;
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_adaptive_kernel, kBlock, 0);
+	if (per_sm < 1) per_sm = 1;
+	unsigned long long blocks_needed = ((unsigned long long)p.n_pixels + (kBlock / 32) - 1) / (kBlock / 32);
+	unsigned long long grid = (unsigned long long)sm_count * per_sm;
+	if (blocks_needed < grid) grid = blocks_needed ? blocks_needed : 1;
+	render_adaptive_kernel<<<(unsigned)grid, kBlock, 0, stream>>>(p);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_resolve(const float4* accum, int n_pixels, float* out_rgb, unsigned* out_counts, cudaStream_t stream) {
+	resolve_kernel<<<(n_pixels + 255) / 256, 256, 0, stream>>>(accum, n_pixels, out_rgb, out_counts);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_camera_rays(const DCamera& cam, unsigned long long seed, unsigned sample, int pixel_begin, int pixel_end, double* rays_out,
+                               cudaStream_t stream) {
+	int n = pixel_end - pixel_begin;
+	if (n <= 0) return cudaSuccess;
+	camera_rays_kernel<<<(n + 127) / 128, 128, 0, stream>>>(cam, seed, sample, pixel_begin, pixel_end, rays_out);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_path_radiance(const DeviceScene& sc, const DCamera& cam, unsigned long long seed, const unsigned* pixel,
+                                 const unsigned* sample, size_t n, float* out_rgb, cudaStream_t stream) {
+	if (n == 0) return cudaSuccess;
+	path_radiance_kernel<<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, stream>>>(sc, cam, seed, pixel, sample, n, out_rgb);
+	return cudaGetLastError();
+}
+
+}  // namespace gs
