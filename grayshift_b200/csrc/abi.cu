@@ -372,7 +372,7 @@ int gs_scene_create(const gs_scene_desc* d, int device, gs_scene** out) {
 						refs.push_back(GS_PRIM_REF(1u, quad_new[idx]));
 					}
 				}
-				if (first >= (1u << 27)) return fail(GS_ERR_UNSUPPORTED, "too many primitive references");
+				if (first >= (1u << 27) - 1u) return fail(GS_ERR_UNSUPPORTED, "too many primitive references");
 				s->h_leaf_code[n] = leaf_code(first, (uint32_t)nd.ref_count);
 			} else { stack.push_back(nd.right); stack.push_back(nd.left); }
 		}

@@ -32,7 +32,9 @@ struct __align__(16) DNode {
 };
 // leaf code: -1 - ((first_ref << 4) | count), count <= 15
 __host__ __device__ inline int leaf_code(uint32_t first, uint32_t count) { return -1 - (int)((first << 4) | count); }
-constexpr int kStackSentinel = 0x7fffffff;
+// Negative (so the inner "internal node" loop stops on it) and not a valid leaf code: it would need
+// first_ref = 2^27 - 1 with count 15, which gs_scene_create rejects.
+constexpr int kStackSentinel = -2147483647 - 1;
 constexpr int kMaxStack = 64;
 
 struct __align__(16) DSphere { double cx, cy, cz, r; };  // r < 0: moving, |r| is the radius
