@@ -73,8 +73,9 @@ class HostScene:
 
 
 def fixed_spp(settings):
-    """Samples per pixel that SampleSettings with tolerance == 0 yields (src/camera.rs:153-164)."""
-    return settings.batch_size * (settings.max_samples // settings.batch_size + 1)
+    """batch_size when the settings give a fixed per-pixel count (max_samples < batch_size: the loop of
+    src/camera.rs:135-165 always leaves after its first batch), else None (adaptive)."""
+    return settings.batch_size if settings.max_samples < settings.batch_size else None
 
 
 class DeviceScene:

@@ -599,11 +599,11 @@ int gs_render(gs_scene* s, const gs_camera* camera, const gs_sample_settings* se
 	cudaEvent_t e0, e1;
 	GS_CUDA(cudaEventCreate(&e0)); GS_CUDA(cudaEventCreate(&e1));
 	GS_CUDA(cudaEventRecord(e0, 0));
-	if (settings->tolerance == 0.0) {
-		// `convergence_sq < 0` never holds, so batches run until sample_count > max_samples (camera.rs:153-164)
-		const uint64_t spp = (uint64_t)settings->batch_size * ((uint64_t)settings->max_samples / settings->batch_size + 1);
-		if (spp > 0xffffffffull) return fail(GS_ERR_UNSUPPORTED, "sample count does not fit 32 bits");
-		rc = gs_render_accumulate(s, camera, seed, 0, (uint32_t)spp, s->accum.p, nullptr);
+	if (settings->max_samples < settings->batch_size) {
+		// After the first batch `sample_count as u32 > max_samples` holds whatever the convergence test says
+		// (camera.rs:153-164): exactly batch_size samples per pixel -> the fixed-count megakernel.  (tolerance
+		// == 0 alone is not enough: on constant pixels the variance rounds below zero and `x < 0` stops early.)
+		rc = gs_render_accumulate(s, camera, seed, 0, settings->batch_size, s->accum.p, nullptr);
 	} else {
 		rc = gs_render_adaptive_accumulate(s, camera, settings, seed, 0, 1, s->accum.p, nullptr);
 	}

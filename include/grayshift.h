@@ -180,8 +180,9 @@ typedef struct gs_camera {
 	double hdri_rotation[3];      /* radians, util.rs:67-70 */
 } gs_camera;
 
-/* SampleSettings, src/camera.rs:239-244 (public fields, same meaning).  tolerance == 0 gives the
- * fixed count batch_size * (max_samples / batch_size + 1) per pixel (camera.rs:153-164). */
+/* SampleSettings, src/camera.rs:239-244 (public fields, same meaning).  max_samples < batch_size
+ * gives exactly batch_size samples per pixel (the loop of camera.rs:135-165 always leaves after its
+ * first batch); the BASELINE.json configs use {batch_size: spp, tolerance: 0, max_samples: 0}. */
 typedef struct gs_sample_settings {
 	double confidence;
 	double tolerance;

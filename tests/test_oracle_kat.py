@@ -73,7 +73,9 @@ def test_moving_sphere_center(tmp_path):  # sphere.rs:51-53
 
 # ---- quad.rs:25-38, 84-109; plane.rs:15-32 -----------------------------------------------------------
 def test_quad_hit_known_answer(tmp_path):
-    s = scene_from(tmp_path, lambda g: g.bvh([g.quad([0, 0, 0], [2, 0, 0], [0, 2, 0], g.lambertian_color([1, 1, 1]))]))
+    # a bare HittableList root: no AABB test in front of the quad (an axis-parallel ray lying exactly in a box
+    # face is rejected by AABB::hit's NaN handling, AABB.rs:62-75, which would mask the quad's own edge rule)
+    s = scene_from(tmp_path, lambda g: g.list([g.quad([0, 0, 0], [2, 0, 0], [0, 2, 0], g.lambertian_color([1, 1, 1]))]))
     rays = np.array([
         [0.5, 1.5, 5, 0, 0, -1, 0],    # interior: alpha .25, beta .75
         [0.0, 0.0, 5, 0, 0, -1, 0],    # corner q: alpha = beta = 0 -> inclusive [0,1] accepts
@@ -170,7 +172,7 @@ def test_bvh_matches_brute_force(tmp_path):
     p = g.write(str(tmp_path / "b.gsg"), g.bvh(items))
     s = orc.OracleScene.load(p)
     o = (rng.random((4000, 3)) - 0.5) * 40
-    d = rng.normal(size=(4000, 3))
+    d = -o + rng.normal(size=(4000, 3)) * 6  # aimed roughly at the cloud
     rays = np.concatenate([o, d, rng.random((4000, 1))], 1)
     ids, t = s.trace_closest(rays)
     bid, bt = brute_force(prims, rays, 0.001, 1.7976931348623157e308)
@@ -406,10 +408,16 @@ def test_fixed_spp_mapping_and_adaptive_rules(tmp_path):
     s = scene_from(tmp_path, build)
     _, counts, ctr, _ = s.render()
     assert np.all(counts == 5) and ctr["paths"] == 5 * 64           # tol 0, max 0: exactly one batch
+    # With max_samples >= batch_size the loop runs until n > max (Q4) wherever the luminance varies.  Where it
+    # is constant (pure background) `sq_sum - sum*sum/n` rounds to a tiny negative number now and then, and
+    # `negative < 0` stops the pixel early even at tolerance 0 -- so only max_samples < batch_size is a true
+    # fixed count, which is what the configs use.
     s.set_sampling(tolerance=0.0, batch_size=5, max_samples=12)
-    assert np.all(s.render()[1] == 15)                               # n > max: 5, 10, 15 (Q4)
+    c = s.render()[1]
+    assert c[4, 4] == 15 and set(np.unique(c)) <= {5, 10, 15}         # n > max: 5, 10, 15
     s.set_sampling(tolerance=0.0, batch_size=32, max_samples=1000)
-    assert np.all(s.render()[1] == 1024)                             # 32 * 32 = 1024
+    c = s.render()[1]
+    assert c[4, 4] == 1024 and c.max() == 1024                        # 32 * 32 = 1024
     # constant-radiance pixels (pure background) have zero variance: 0 < mean^2 tol^2 stops after one batch;
     # black pixels (mean 0) never satisfy 0 < 0 and run to the cap
     s.set_sampling(tolerance=0.25, batch_size=4, max_samples=20)
