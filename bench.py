@@ -1,0 +1,291 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: paths/s (and Mrays/s) of the path-tracing hot path on the Book-2 final
+scene (BASELINE.json config 4: 800x800, max_depth 40), on N B200s of one node.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--config c4] [--spp-per-step S]
+
+A "step" is one pass of the hot path over one batch: `spp-per-step` samples of EVERY pixel of the full-size
+config (default 500; 20 steps = the config's 10000 spp = 6.4 G paths).  Throughput is independent of the
+number of steps.  With N ranks every rank renders its own sample slices (weak scaling: per-GPU work fixed)
+and the W*H float4 accumulators are summed with NCCL after each step, inside the timed region.
+
+value     : paths/s over all ranks, scene resident in HBM, device time (CUDA events), max over ranks.
+e2e       : the same metric through the C ABI with HOST buffers: gs_scene_create (scene H2D) + render +
+            accumulator reduce + gs_resolve (image D2H) every step, wall clock bracketed by synchronizes.
+roofline  : HBM-bound model; achieved = rays/s x algorithmic bytes per ray (bench_constants.json, frozen
+            from the oracle's reference-semantics counters: 32 B per box test, 32 B per primitive test,
+            16 B per texel), peak = MEASURED_PEAKS.json hbm_gbs.
+--impl reference : the CPU restatement of the reference (oracle/, C++ port of the Rust) on all host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FULL_SPP = {"c1": 100, "c2": 1000, "c3": 1000, "c4": 10000, "c5": 4096}
+WORKLOAD = {
+    "c1": "Book-1 random spheres (config 1), 400x225, max_depth 50",
+    "c2": "earthmap sphere + airport.hdr (config 2), 1280x720, max_depth 50",
+    "c3": "Cornell box (config 3), 600x600, max_depth 50",
+    "c4": "Book-2 final scene (config 4): BVH over 2400 box quads + 1005 spheres, 2 constant media, Perlin + image textures, 800x800, max_depth 40",
+    "c5": "1M random spheres (config 5), 3840x2160, max_depth 50",
+}
+
+
+def constants():
+    with open(os.path.join(ROOT, "bench_constants.json")) as f:
+        return json.load(f)
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=lambda: [self.lines.append(ln) for ln in self.proc.stdout], daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(config, target_seconds=12.0):
+    """The oracle (C++ port of the Rust reference) on all host cores, bounded sample of the same workload."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_ffi as orc
+
+    cores = os.cpu_count() or 1
+    probe = orc.OracleScene.build(config, spp=1)
+    _, _, c, sec = probe.render(seed=1, rng=orc.OracleScene.WYRAND, threads=cores)
+    rate = c["paths"] / sec
+    spp = max(1, min(64, int(target_seconds * rate / (probe.width * probe.height))))
+    s = orc.OracleScene.build(config, spp=spp)
+    _, _, c, sec = s.render(seed=2, rng=orc.OracleScene.WYRAND, threads=cores)
+    return {"value": c["paths"] / sec, "unit": "paths/s", "cores": cores, "kind": "port", "mrays_per_s": c["rays"] / sec / 1e6,
+            "sample": f"{config} at full resolution {s.width}x{s.height}, {spp} spp ({c['paths']} paths, {sec:.1f} s), C++ port of the Rust reference, "
+                      f"{cores} threads, Wyrand RNG"}
+
+
+def run_reference(args):
+    """--impl reference: times the CPU port on this box's host cores, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_ffi as orc
+
+    cores = os.cpu_count() or 1
+    probe = orc.OracleScene.build(args.config, spp=1)
+    _, _, c, sec = probe.render(seed=1, rng=orc.OracleScene.WYRAND, threads=cores)
+    rate = c["paths"] / sec
+    total = max(1, args.steps + args.warmup)
+    per_step_s = min(6.0, 150.0 / total)
+    spp = max(1, int(per_step_s * rate / (probe.width * probe.height)))
+    s = orc.OracleScene.build(args.config, spp=spp)
+    for w in range(args.warmup):
+        s.render(seed=100 + w, rng=orc.OracleScene.WYRAND, threads=cores)
+    paths = rays = 0
+    secs = 0.0
+    for k in range(args.steps):
+        _, _, c, sec = s.render(seed=200 + k, rng=orc.OracleScene.WYRAND, threads=cores)
+        paths += c["paths"]; rays += c["rays"]; secs += sec
+    value = paths / secs
+    line = {"impl": "reference", "metric": "paths/s", "value": value, "unit": "paths/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "mrays_per_s": rays / secs / 1e6,
+            "config": {"workload": WORKLOAD[args.config], "samples_per_pixel_per_step": spp, "scene_seed": 1},
+            "cpu_baseline": {"value": value, "unit": "paths/s", "cores": cores, "kind": "port",
+                             "sample": f"{args.config} full resolution {s.width}x{s.height}, {spp} spp per step, {args.steps} steps; C++ port of the Rust "
+                                       f"reference (the Rust itself cannot be built: no cargo/rustc), {cores} threads"},
+            "e2e": {"value": value, "unit": "paths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="grayshift_b200")
+    ap.add_argument("--config", default="c4", choices=sorted(WORKLOAD))
+    ap.add_argument("--spp-per-step", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--pipeline", default="megakernel", choices=["megakernel", "wavefront"],
+                    help="device pipeline (the megakernel is the default, chosen from ncu evidence; see DESIGN.md section 6)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import grayshift_b200 as gs
+    from grayshift_b200 import dist as gdist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    spp_step = args.spp_per_step or {"c1": 100, "c2": 200, "c3": 250, "c4": 500, "c5": 16}[args.config]
+    host = gs.HostScene.build(args.config, spp=spp_step)
+    t0 = time.perf_counter()
+    host.flatten()
+    flatten_s = time.perf_counter() - t0
+    scene = gs.DeviceScene(host, device=local_rank)
+    scene.set_option("wavefront", 1 if args.pipeline == "wavefront" else 0)
+    W, H = scene.width, scene.height
+    n_px = W * H
+    accum = torch.zeros((n_px, 4), dtype=torch.float32, device=device)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)  # > 126 MB L2
+    stream = torch.cuda.current_stream(device)
+
+    def step(k):
+        begin = (k * world + rank) * spp_step  # disjoint global sample slices
+        scene.render_accumulate(accum.data_ptr(), seed=1, sample_begin=begin, sample_count=spp_step, stream=stream.cuda_stream)
+        if world > 1:
+            gdist.reduce_accumulators(accum, dst=0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    for w in range(args.warmup):
+        step(w)
+    barrier()
+    scene.stats()  # reset device counters
+    accum.zero_()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    barrier()
+    wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.zero_()  # L2 flush between timed iterations (not timed)
+        starts[k].record(stream)
+        step(args.warmup + k)
+        ends[k].record(stream)
+    barrier()
+    wall = time.perf_counter() - wall0
+    clk = clocks.stop() if rank == 0 else None
+    step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=device)
+    st = scene.stats()
+    counts = torch.tensor([float(st.paths), float(st.rays)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+    total_s = float(total_ms.item()) * 1e-3
+    paths, rays = float(counts[0].item()), float(counts[1].item())
+
+    # ---- end to end through the C ABI with host buffers ----
+    e2e_steps = max(1, min(args.e2e_steps, args.steps))
+    h2d = d2h = 0
+    barrier()
+    e0 = time.perf_counter()
+    for k in range(e2e_steps):
+        sc2 = gs.DeviceScene(host, device=local_rank)                 # gs_scene_create: scene arrays host -> device
+        sc2.set_option("wavefront", 1 if args.pipeline == "wavefront" else 0)
+        acc2 = torch.zeros((n_px, 4), dtype=torch.float32, device=device)
+        begin = ((args.warmup + args.steps + k) * world + rank) * spp_step
+        sc2.render_accumulate(acc2.data_ptr(), seed=1, sample_begin=begin, sample_count=spp_step, stream=stream.cuda_stream)
+        if world > 1:
+            gdist.reduce_accumulators(acc2, dst=0)
+        if rank == 0:
+            rgb, cnt = sc2.resolve(acc2.data_ptr(), stream=stream.cuda_stream)  # image device -> host
+            d2h = rgb.nbytes + cnt.nbytes
+        st2 = sc2.stats()
+        h2d = int(st2.h2d_bytes) + 512  # scene arrays + camera/settings structs
+        sc2.close()
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - e0], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = (n_px * spp_step * world * e2e_steps) / float(e2e_s.item())
+
+    if rank == 0:
+        k = constants()[args.config]
+        peak, peak_src = measured_peak()
+        # dominant kernel = render_fixed_kernel, one launch per step per GPU; per-GPU figures for the roofline
+        rays_per_launch = rays / (args.steps * world)
+        launch_s = total_s / args.steps
+        achieved = rays_per_launch * k["bytes_per_ray"] / launch_s / 1e9
+        line = {
+            "metric": "paths/s", "value": paths / total_s, "unit": "paths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64 primitive intersection + f32 boxes/shading", "data": "synthetic",
+            "mrays_per_s": rays / total_s / 1e6, "rays_per_path": rays / paths,
+            "config": {"workload": WORKLOAD[args.config], "samples_per_pixel_per_step": spp_step, "full_config_spp": FULL_SPP[args.config],
+                       "scene_seed": 1, "render_seed": 1, "l2": "flushed between timed steps (256 MiB write); scene working set itself is L2-resident",
+                       "parallelism": f"spp-split x{world}, NCCL reduce of the fp32 accumulator each step" if world > 1 else "single GPU",
+                       "bvh": "binned SAH, binary, <=4 prims/leaf", "pipeline": args.pipeline, "host_flatten_s": round(flatten_s, 3)},
+            "e2e": {"value": e2e_value, "unit": "paths/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                    "what": "gs_scene_create + gs_render_accumulate + reduce + gs_resolve to host, per step"},
+            "gpu_launches": int(st.kernel_launches) * world,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peak_src, "kernel": "render_fixed_kernel" if args.pipeline == "megakernel" else "wf_traverse_kernel + wf_shade_kernel + wf_generate_kernel",
+                         "algorithmic_bytes_per_ray": k["bytes_per_ray"],
+                         "note": "algorithmic bytes = reference-semantics box/prim/texel counts x 32/32/16 B; the scene is L1/L2 resident, so this is a "
+                                 "model of work, not DRAM traffic (see profiles/ for dram__bytes and L2 throughput)"},
+            "clocks": clk, "wall_s_timed_region": wall,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(args.config)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

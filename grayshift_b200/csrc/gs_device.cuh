@@ -87,8 +87,15 @@ struct DCamera {
 // Philox4x32-10, counter = (pixel, sample, block, stream), key = seed.  Draw k of a path is
 // word k&3 of block k>>2 (the oracle uses the identical scheme).
 // ------------------------------------------------------------------------------------------
+// (An out-of-line copy was tried to shrink the megakernel's code: it cost 60 registers around the calls, so the
+// rounds stay inline and rolled up: 10 iterations of 8 instructions instead of 25 inlined copies of 80.)
 __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
-#pragma unroll
+#ifndef GS_PHILOX_UNROLL
+#define GS_PHILOX_UNROLL 1  // tuning knob: 1 = rolled loop (small code), 10 = fully unrolled
+#endif
+#define GS_STR_(x) #x
+#define GS_PRAGMA_UNROLL_(n) _Pragma(GS_STR_(unroll n))
+	GS_PRAGMA_UNROLL_(GS_PHILOX_UNROLL)
 	for (int r = 0; r < 10; ++r) {
 		uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
 		uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
@@ -131,10 +138,12 @@ struct Hit {
 };
 constexpr uint32_t kNoHit = 0xffffffffu;
 
-// Sphere::hit, sphere.rs:64-92.  `a` = |d|^2 is hoisted out by the caller (ray constant).
-// strict interval (surrounds, interval.rs:33-35).
+// Sphere::hit, sphere.rs:64-92.  `a` = |d|^2 and its reciprocal are hoisted out by the caller (ray constants):
+// the two roots (h -+ sqrt(disc)) / a become multiplications by 1/a (one f64 division per ray instead of up to
+// two per candidate; differs from the reference's quotient by at most 1 ulp).  Strict interval (surrounds,
+// interval.rs:33-35).
 __device__ __forceinline__ bool hit_sphere(const DSphere& s, const double4* __restrict__ path, uint32_t index, const Ray& r, double a,
-                                           double tmin, double tmax, double& t_out) {
+                                           double inv_a, double tmin, double tmax, double& t_out) {
 	double cx = s.cx, cy = s.cy, cz = s.cz, rad = s.r;
 	if (rad < 0.0) {  // moving: center_start + time * center_path (sphere.rs:51-53)
 		double4 p = path[index];
@@ -147,9 +156,9 @@ __device__ __forceinline__ bool hit_sphere(const DSphere& s, const double4* __re
 	double disc = h * h - a * c;
 	if (disc < 0.0) return false;
 	double sq = sqrt(disc);
-	double t = (h - sq) / a;
+	double t = (h - sq) * inv_a;
 	if (!(tmin < t && t < tmax)) {
-		t = (h + sq) / a;
+		t = (h + sq) * inv_a;
 		if (!(tmin < t && t < tmax)) return false;
 	}
 	t_out = t;
@@ -183,87 +192,131 @@ __device__ __forceinline__ DQuad load_quad(const DQuad* __restrict__ p, uint32_t
 
 __device__ __forceinline__ float safe_rcp(float d) {
 	// 1/0 = inf in the reference (AABB.rs:64); a huge finite inverse orders the slabs identically without NaNs
+	// (1e25 keeps origin * inverse finite for any origin the padded boxes allow)
 	float ad = fabsf(d);
-	return ad < 1e-30f ? copysignf(1e30f, d) : 1.0f / d;
+	return ad < 1e-25f ? copysignf(1e25f, d) : 1.0f / d;
 }
 
 // ------------------------------------------------------------------------------------------
 // Closest hit over the surface BVH: BVHNode::hit + AABB::hit + HittableList::hit collapsed into an
 // ordered while-while traversal with a per-thread stack.  Result equals the reference's
-// unordered recursion (BVH.rs:68-90) except on exact ties.
+// unordered recursion (BVH.rs:68-90); exact ties follow the reference's visiting order (Q9).
+//
+// The traversal is RESUMABLE: its whole state is (node, sp, best, stack), so the render megakernel
+// can leave the loop when enough lanes of the warp have finished their ray, shade / regenerate
+// those lanes, and re-enter with the unfinished rays exactly where they stopped (ncu on the first
+// version showed 8.4 of 32 lanes active in the node loop: lanes idled until the warp's longest ray ended).
 // ------------------------------------------------------------------------------------------
-template <bool kCount>
-__device__ __forceinline__ Hit trace_closest(const DeviceScene& sc, const Ray& r, double tmin, double tmax, uint32_t* node_visits = nullptr) {
+struct TravState {
+	int node;   // current node index / leaf code, kStackSentinel when the ray is finished
+	int sp;     // stack entries in use
 	Hit best;
-	best.t = tmax; best.ref = kNoHit; best.u = 0.0; best.v = 0.0;
-	const float ox = (float)r.ox, oy = (float)r.oy, oz = (float)r.oz;
-	const float idx = safe_rcp((float)r.dx), idy = safe_rcp((float)r.dy), idz = safe_rcp((float)r.dz);
-	const double a = r.dx * r.dx + r.dy * r.dy + r.dz * r.dz;  // length_squared (sphere.rs:71)
-	float tmax32 = tmax >= 3.0e38 ? 3.4028235e38f : __double2float_ru(tmax);
+};
 
-	int stack[kMaxStack];
-	int sp = 0;
-	stack[sp++] = kStackSentinel;
-	int node = sc.root;
+struct RayConsts {  // per-ray values derived from the Ray; recomputed whenever a traversal is (re)entered
+	float idx, idy, idz;     // 1 / direction
+	float oix, oiy, oiz;     // origin * (1 / direction): slab distance = fma(plane, id, -oi)
+	float tmax32;            // fp32 upper bound of the current closest t, for box culling
+	double a, inv_a;         // |d|^2, Vec3::length_squared (sphere.rs:71), and its reciprocal
+};
 
-	while (node != kStackSentinel) {
-		while (node >= 0) {
-			const float4* np = reinterpret_cast<const float4*>(sc.nodes + node);
-			const float4 xy0 = __ldg(np), xy1 = __ldg(np + 1), z01 = __ldg(np + 2);
-			const int4 link = __ldg(reinterpret_cast<const int4*>(np + 3));
-			if (kCount) ++(*node_visits);
-			// child 0
-			float t0 = (xy0.x - ox) * idx, t1 = (xy0.y - ox) * idx;
-			float t2 = (xy0.z - oy) * idy, t3 = (xy0.w - oy) * idy;
-			float t4 = (z01.x - oz) * idz, t5 = (z01.y - oz) * idz;
-			float en0 = fmaxf(fmaxf(fminf(t0, t1), fminf(t2, t3)), fmaxf(fminf(t4, t5), 0.0f));
-			float ex0 = fminf(fminf(fmaxf(t0, t1), fmaxf(t2, t3)), fminf(fmaxf(t4, t5), tmax32));
-			// child 1
-			t0 = (xy1.x - ox) * idx; t1 = (xy1.y - ox) * idx;
-			t2 = (xy1.z - oy) * idy; t3 = (xy1.w - oy) * idy;
-			t4 = (z01.z - oz) * idz; t5 = (z01.w - oz) * idz;
-			float en1 = fmaxf(fmaxf(fminf(t0, t1), fminf(t2, t3)), fmaxf(fminf(t4, t5), 0.0f));
-			float ex1 = fminf(fminf(fmaxf(t0, t1), fmaxf(t2, t3)), fminf(fmaxf(t4, t5), tmax32));
-			const bool h0 = en0 <= ex0, h1 = en1 <= ex1;
-			if (!h0 && !h1) { node = stack[--sp]; }
-			else {
-				int near = link.x, far = link.y;
-				if (h0 && h1) {
-					if (en1 < en0) { int tmp = near; near = far; far = tmp; }
-					stack[sp++] = far;
-					node = near;
-				} else node = h0 ? near : far;
+__device__ __forceinline__ float tmax_to_f32(double t) { return t >= 3.0e38 ? 3.4028235e38f : __double2float_ru(t); }
+
+__device__ __forceinline__ RayConsts ray_consts(const Ray& r, double t_closest) {
+	RayConsts c;
+	c.idx = safe_rcp((float)r.dx); c.idy = safe_rcp((float)r.dy); c.idz = safe_rcp((float)r.dz);
+	c.oix = (float)r.ox * c.idx; c.oiy = (float)r.oy * c.idy; c.oiz = (float)r.oz * c.idz;
+	c.a = r.dx * r.dx + r.dy * r.dy + r.dz * r.dz;
+	c.inv_a = 1.0 / c.a;
+	c.tmax32 = tmax_to_f32(t_closest);
+	return c;
+}
+
+__device__ __forceinline__ void trav_init(const DeviceScene& sc, TravState& tv, int* stack, double tmax) {
+	stack[0] = kStackSentinel;
+	tv.sp = 1;
+	tv.node = sc.root;
+	tv.best.t = tmax; tv.best.ref = kNoHit; tv.best.u = 0.0; tv.best.v = 0.0;
+}
+
+// One internal node: AABB::hit (AABB.rs:58-113) for both children at once, near child first, far child pushed.
+// Slab distances in fp32 as fma(plane, 1/d, -o/d) against boxes padded by 8 ulp of the origin range
+// (abi.cu build_nodes): conservative, never culls a true hit.  Precondition: tv.node >= 0.
+template <bool kCount>
+__device__ __forceinline__ void node_step(const DeviceScene& sc, const RayConsts& rc, TravState& tv, int* stack, uint32_t* node_visits) {
+	const float4* np = reinterpret_cast<const float4*>(sc.nodes + tv.node);
+	const float4 xy0 = __ldg(np), xy1 = __ldg(np + 1), z01 = __ldg(np + 2);
+	const int4 link = __ldg(reinterpret_cast<const int4*>(np + 3));
+	if (kCount) ++(*node_visits);
+	float t0 = fmaf(xy0.x, rc.idx, -rc.oix), t1 = fmaf(xy0.y, rc.idx, -rc.oix);
+	float t2 = fmaf(xy0.z, rc.idy, -rc.oiy), t3 = fmaf(xy0.w, rc.idy, -rc.oiy);
+	float t4 = fmaf(z01.x, rc.idz, -rc.oiz), t5 = fmaf(z01.y, rc.idz, -rc.oiz);
+	const float en0 = fmaxf(fmaxf(fminf(t0, t1), fminf(t2, t3)), fmaxf(fminf(t4, t5), 0.0f));
+	const float ex0 = fminf(fminf(fmaxf(t0, t1), fmaxf(t2, t3)), fminf(fmaxf(t4, t5), rc.tmax32));
+	t0 = fmaf(xy1.x, rc.idx, -rc.oix); t1 = fmaf(xy1.y, rc.idx, -rc.oix);
+	t2 = fmaf(xy1.z, rc.idy, -rc.oiy); t3 = fmaf(xy1.w, rc.idy, -rc.oiy);
+	t4 = fmaf(z01.z, rc.idz, -rc.oiz); t5 = fmaf(z01.w, rc.idz, -rc.oiz);
+	const float en1 = fmaxf(fmaxf(fminf(t0, t1), fminf(t2, t3)), fmaxf(fminf(t4, t5), 0.0f));
+	const float ex1 = fminf(fminf(fmaxf(t0, t1), fmaxf(t2, t3)), fminf(fmaxf(t4, t5), rc.tmax32));
+	const bool h0 = en0 <= ex0, h1 = en1 <= ex1;
+	if (!h0 && !h1) { tv.node = stack[--tv.sp]; }
+	else {
+		int near = link.x, far = link.y;
+		if (h0 && h1) {
+			if (en1 < en0) { int tmp = near; near = far; far = tmp; }
+			stack[tv.sp++] = far;
+			tv.node = near;
+		} else tv.node = h0 ? near : far;
+	}
+}
+
+// One leaf: HittableList::hit over its primitives (hittable.rs:70-86) with the reference's interval rules, then pop.
+// Precondition: tv.node is a leaf code.
+__device__ __forceinline__ void leaf_step(const DeviceScene& sc, const Ray& r, RayConsts& rc, double tmin, TravState& tv, int* stack) {
+	Hit& best = tv.best;
+	const uint32_t code = (uint32_t)(-1 - tv.node);
+	const uint32_t first = code >> 4, count = code & 15u;
+	for (uint32_t k = 0; k < count; ++k) {
+		const uint32_t ref = __ldg(sc.refs + first + k);
+		const uint32_t index = ref & kRefIndexMask;
+		if ((ref >> kRefKindShift) == 0u) {
+			const DSphere s = load_sphere(sc.spheres, index);
+			double t;
+			if (hit_sphere(s, sc.sph_path, index, r, rc.a, rc.inv_a, tmin, best.t, t)) { best.t = t; best.ref = ref; }
+		} else {
+			const DQuad q = load_quad(sc.quads, index);
+			double t, al, be;
+			if (hit_quad(q, r, tmin, best.t, t, al, be)) {
+				// exact tie between two quads: the one the reference visits later wins (t <= closest, plane.rs:27)
+				bool accept = true;
+				if (t == best.t && best.ref != kNoHit && (best.ref >> kRefKindShift) == 1u)
+					accept = __ldg(sc.quad_order + index) > __ldg(sc.quad_order + (best.ref & kRefIndexMask));
+				if (accept) { best.t = t; best.ref = ref; best.u = al; best.v = be; }
 			}
-		}
-		if (node == kStackSentinel) break;
-		// leaf
-		{
-			const uint32_t code = (uint32_t)(-1 - node);
-			const uint32_t first = code >> 4, count = code & 15u;
-			for (uint32_t k = 0; k < count; ++k) {
-				const uint32_t ref = __ldg(sc.refs + first + k);
-				const uint32_t index = ref & kRefIndexMask;
-				if ((ref >> kRefKindShift) == 0u) {
-					const DSphere s = load_sphere(sc.spheres, index);
-					double t;
-					if (hit_sphere(s, sc.sph_path, index, r, a, tmin, best.t, t)) { best.t = t; best.ref = ref; }
-				} else {
-					const DQuad q = load_quad(sc.quads, index);
-					double t, al, be;
-					if (hit_quad(q, r, tmin, best.t, t, al, be)) {
-						// exact tie between two quads: the one the reference visits later wins (t <= closest, plane.rs:27)
-						bool accept = true;
-						if (t == best.t && best.ref != kNoHit && (best.ref >> kRefKindShift) == 1u)
-							accept = __ldg(sc.quad_order + index) > __ldg(sc.quad_order + (best.ref & kRefIndexMask));
-						if (accept) { best.t = t; best.ref = ref; best.u = al; best.v = be; }
-					}
-				}
-			}
-			if (best.ref != kNoHit) tmax32 = __double2float_ru(best.t);
-			node = stack[--sp];
 		}
 	}
-	return best;
+	if (best.ref != kNoHit) rc.tmax32 = __double2float_ru(best.t);
+	tv.node = stack[--tv.sp];
+}
+
+// One round of the classic while-while traversal: descend to the next leaf, intersect it.
+// Precondition: tv.node != kStackSentinel.
+template <bool kCount>
+__device__ __forceinline__ void trav_round(const DeviceScene& sc, const Ray& r, RayConsts& rc, double tmin, TravState& tv, int* stack,
+                                           uint32_t* node_visits) {
+	while (tv.node >= 0) node_step<kCount>(sc, rc, tv, stack, node_visits);
+	if (tv.node != kStackSentinel) leaf_step(sc, r, rc, tmin, tv, stack);
+}
+
+// Run-to-completion form (parity kernel, adaptive kernel, per-path hooks).
+template <bool kCount>
+__device__ __forceinline__ Hit trace_closest(const DeviceScene& sc, const Ray& r, double tmin, double tmax, uint32_t* node_visits = nullptr) {
+	int stack[kMaxStack];
+	TravState tv;
+	trav_init(sc, tv, stack, tmax);
+	RayConsts rc = ray_consts(r, tmax);
+	while (tv.node != kStackSentinel) trav_round<kCount>(sc, r, rc, tmin, tv, stack, node_visits);
+	return tv.best;
 }
 
 }  // namespace gs

@@ -41,4 +41,42 @@ cudaError_t launch_trace_closest(const DeviceScene& sc, const double* rays, size
                                  cudaStream_t stream);
 int render_fixed_blocks_per_sm(bool count_nodes);
 
+// ---- wavefront pipeline (wavefront_kernels.cu) -------------------------------------------------------
+// Path pool: structure of arrays in HBM, one slot per in-flight path, every field a 16-byte record so each
+// access is one 128-bit load/store and consecutive slots coalesce.
+struct PathPool {
+	double4* org;   // ray origin x, y, z, time
+	double4* dir;   // ray direction x, y, z, closest t found by the traversal (surface hit or medium event)
+	float4* thr;    // throughput (prod of attenuations) r, g, b, -
+	float4* rad;    // radiance so far r, g, b, -
+	uint4* ids;     // pixel, sample, draw counter, bounce | kSlotActive
+	uint4* hit;     // primitive ref (kNoHit = none), medium index (-1 = none), u bits, v bits
+	int n;
+};
+constexpr unsigned kSlotActive = 0x80000000u;
+
+struct WaveCounters {              // one small device struct per scene
+	unsigned long long next_item;  // next (pixel, sample) item to start
+	unsigned next_ray;             // traverse kernel: next slot to fetch
+	unsigned n_free;               // slots released by the shade kernel of this wave
+	int n_live;                    // slots holding a path
+};
+
+struct WavefrontParams {
+	DeviceScene sc;
+	DCamera cam;
+	PathPool pool;
+	unsigned long long seed;
+	unsigned sample_begin, sample_count;
+	unsigned long long total_items;
+	float4* accum;
+	WaveCounters* ctr;
+	int* free_list;        // slots to (re)generate; nullptr = every slot (first wave)
+	unsigned long long* stats;
+};
+
+cudaError_t launch_wf_generate(const WavefrontParams& p, bool first_wave, cudaStream_t stream);
+cudaError_t launch_wf_traverse(const WavefrontParams& p, int sm_count, bool count_nodes, cudaStream_t stream);
+cudaError_t launch_wf_shade(const WavefrontParams& p, cudaStream_t stream);
+
 }  // namespace gs

@@ -85,21 +85,13 @@ __device__ __forceinline__ f3 background(const DeviceScene& sc, const DCamera& c
 }
 
 // ---- Perlin (noise 0.9.0, restated; see oracle.cpp) on a shared-memory permutation table ------------
+// Ken Perlin's 12 edge gradients selected by hash & 15 (12..15 alias 0, 9, 1, 11), branch-free: the 16-way
+// switch was inlined 8 times per octave and made up a fifth of the kernel's code.
 __device__ __forceinline__ float perlin_grad(uint32_t h, float x, float y, float z) {
-	switch (h & 15u) {
-		case 0: case 12: return x + y;
-		case 1: case 14: return -x + y;
-		case 2: return x - y;
-		case 3: return -x - y;
-		case 4: return x + z;
-		case 5: return -x + z;
-		case 6: return x - z;
-		case 7: return -x - z;
-		case 8: return y + z;
-		case 9: case 13: return -y + z;
-		case 10: return y - z;
-		default: return -y - z;
-	}
+	h &= 15u;
+	const float u = h < 8u ? x : y;
+	const float v = h < 4u ? y : ((h == 12u || h == 14u) ? x : z);
+	return ((h & 1u) ? -u : u) + ((h & 2u) ? -v : v);
 }
 __device__ __forceinline__ float perlin_get(const uint8_t* __restrict__ perm, double px, double py, double pz) {
 	double fx = floor(px), fy = floor(py), fz = floor(pz);
@@ -173,7 +165,11 @@ __device__ __forceinline__ f3 texture_value(const DeviceScene& sc, const uint8_t
 				weight *= 0.5f;
 				sx *= 2.0; sy *= 2.0; sz *= 2.0;
 			}
-			float g = 0.5f * (1.0f + sinf((float)(sd.y * s.pz) + 10.0f * fabsf(accum)));
+			// sin of a phase that can reach a few hundred radians: reduce to [-pi, pi] in f64 (cheap, exact enough),
+			// then the SFU sine (abs. error ~1e-6 there); libm's sinf drags in its 280-instruction slow path
+			const double phase = sd.y * s.pz + (double)(10.0f * fabsf(accum));
+			const float red = (float)(phase - 6.283185307179586 * rint(phase * 0.15915494309189535));
+			float g = 0.5f * (1.0f + __sinf(red));
 			return mk3(g, g, g);
 		}
 	}
@@ -245,14 +241,21 @@ __device__ __forceinline__ bool shade(const DeviceScene& sc, const uint8_t* __re
 // Statistically identical to the reference's in-traversal evaluation: the free-flight draw is
 // independent of everything else, so testing the medium first and clipping the surface search at
 // its candidate t gives the same closest-event distribution.
-__device__ __forceinline__ bool boundary_closest(const DeviceScene& sc, const DMedium& m, const Ray& r, double a, double lo, double hi,
-                                                 bool strict_only, double& t_out) {
+#ifndef GS_BOUNDARY_INLINE
+#define GS_BOUNDARY_INLINE 1  // tuning knob: 0 = out-of-line (smaller code, but the call spills ~600 B of registers)
+#endif
+#if GS_BOUNDARY_INLINE
+__device__ __forceinline__
+#else
+static __device__ __noinline__
+#endif
+bool boundary_closest(const DeviceScene& sc, const DMedium& m, const Ray& r, double a, double inv_a, double lo, double hi, double& t_out) {
 	bool found = false;
 	double best = hi;
 	for (int k = 0; k < m.sph_count; ++k) {
 		DSphere s = load_sphere(sc.bnd_spheres, m.sph_first + k);
 		double t;
-		if (hit_sphere(s, sc.bnd_sph_path, m.sph_first + k, r, a, lo, best, t)) { best = t; found = true; }
+		if (hit_sphere(s, sc.bnd_sph_path, m.sph_first + k, r, a, inv_a, lo, best, t)) { best = t; found = true; }
 	}
 	for (int k = 0; k < m.quad_count; ++k) {
 		DQuad q = load_quad(sc.bnd_quads, m.quad_first + k);
@@ -263,20 +266,41 @@ __device__ __forceinline__ bool boundary_closest(const DeviceScene& sc, const DM
 	return found;
 }
 
-__device__ __forceinline__ bool medium_event(const DeviceScene& sc, const DMedium& m, const Ray& r, double a, double tmin, double tmax,
-                                             float u01, double& t_out) {
+__device__ __forceinline__ bool medium_event(const DeviceScene& sc, const DMedium& m, const Ray& r, double a, double inv_a, double tmin,
+                                             double tmax, float u01, double& t_out) {
+	const double kMax = 1.7976931348623157e308;
 	double t1, t2;
-	if (!boundary_closest(sc, m, r, a, -1.7976931348623157e308, 1.7976931348623157e308, false, t1)) return false;  // Interval::UNIVERSE
-	if (!boundary_closest(sc, m, r, a, t1 + 0.0001, 1.7976931348623157e308, false, t2)) return false;
+	if (m.sph_count == 1 && m.quad_count == 0) {
+		// One stationary-or-moving sphere as the boundary (main.rs:714-738): both calls of volume.rs:33-37 are the two
+		// roots of one quadratic.  hit(UNIVERSE) takes the near root (any finite value is inside (-MAX, MAX));
+		// hit([t1 + 1e-4, MAX)) re-tests the near root (fails) and takes the far one if it lies beyond t1 + 1e-4.
+		DSphere s = load_sphere(sc.bnd_spheres, m.sph_first);
+		double cx = s.cx, cy = s.cy, cz = s.cz, rad = s.r;
+		if (rad < 0.0) { double4 p = sc.bnd_sph_path[m.sph_first]; cx += r.time * p.x; cy += r.time * p.y; cz += r.time * p.z; rad = -rad; }
+		double ocx = cx - r.ox, ocy = cy - r.oy, ocz = cz - r.oz;
+		double h = r.dx * ocx + r.dy * ocy + r.dz * ocz;
+		double c = (ocx * ocx + ocy * ocy + ocz * ocz) - rad * rad;
+		double disc = h * h - a * c;
+		if (disc < 0.0) return false;
+		double sq = sqrt(disc);
+		t1 = (h - sq) * inv_a;
+		t2 = (h + sq) * inv_a;
+		if (!(t1 > -kMax && t1 < kMax)) return false;
+		if (!(t1 + 0.0001 < t2 && t2 < kMax)) return false;
+	} else {
+		if (!boundary_closest(sc, m, r, a, inv_a, -kMax, kMax, t1)) return false;  // Interval::UNIVERSE
+		if (!boundary_closest(sc, m, r, a, inv_a, t1 + 0.0001, kMax, t2)) return false;
+	}
 	if (t1 < tmin) t1 = tmin;
 	if (t2 > tmax) t2 = tmax;
 	if (t1 >= t2) return false;
 	if (t1 < 0.0) t1 = 0.0;
-	double ray_len = sqrt(a);
-	double dist_inside = (t2 - t1) * ray_len;
-	double hit_dist = m.neg_inv_density * (double)logf(u01);
-	if (hit_dist > dist_inside) return false;
-	t_out = t1 + hit_dist / ray_len;
+	// volume.rs:46-52 in units of t: hit_dist / ray_len compared with (t2 - t1).  The free-flight length is a random
+	// draw, so it is formed in f32 (24-bit uniform, logf) and only then promoted.
+	const float inv_len = rsqrtf((float)a);
+	const double dt = (double)((float)m.neg_inv_density * logf(u01) * inv_len);
+	if (dt > t2 - t1) return false;
+	t_out = t1 + dt;
 	return true;
 }
 
@@ -300,18 +324,18 @@ __device__ __forceinline__ void path_begin(PathState& st, const DCamera& cam, ui
 	st.bounce = 0;
 }
 
-// One world.hit + emitted + scatter (one level of the reference's recursion).  Returns true when the
-// path is finished (miss, absorbed, light, or depth exhausted); st.L then holds the sample colour.
-template <bool kCount>
-__device__ __forceinline__ bool path_step(const DeviceScene& sc, const DCamera& cam, const uint8_t* __restrict__ perm, PathState& st,
-                                          PathCounters& pc) {
-	if (st.bounce >= cam.max_depth) return true;  // `if depth <= 0 { return ZERO }`, camera.rs:175
-	Ray& ray = st.ray;
+// Start of one level of the reference's recursion: the depth test (camera.rs:175) and the media.  Returns false
+// when the path is finished (depth exhausted).  tmax = the closest medium event (or f64::MAX), medium_hit its index.
+__device__ __forceinline__ bool segment_begin(const DeviceScene& sc, const DCamera& cam, PathState& st, PathCounters& pc, double& tmax,
+                                              int& medium_hit) {
+	if (st.bounce >= cam.max_depth) return false;  // `if depth <= 0 { return ZERO }`
 	++pc.rays;
-	double tmax = 1.7976931348623157e308;  // Interval::new(0.001, f64::MAX), camera.rs:177
-	int medium_hit = -1;
+	tmax = 1.7976931348623157e308;  // Interval::new(0.001, f64::MAX), camera.rs:177
+	medium_hit = -1;
 	if (sc.n_media > 0) {
+		const Ray& ray = st.ray;
 		const double a = ray.dx * ray.dx + ray.dy * ray.dy + ray.dz * ray.dz;
+		const double inv_a = 1.0 / a;
 		// media stream: counter word 3 = 1, block = bounce * 64 + group, 4 media per block
 		uint4 blk = make_uint4(0u, 0u, 0u, 0u);
 		for (int mi = 0; mi < sc.n_media; ++mi) {
@@ -319,10 +343,17 @@ __device__ __forceinline__ bool path_step(const DeviceScene& sc, const DCamera& 
 			uint32_t w = (mi & 3) == 0 ? blk.x : ((mi & 3) == 1 ? blk.y : ((mi & 3) == 2 ? blk.z : blk.w));
 			float u01 = (float)(w >> 8) * (1.0f / 16777216.0f);
 			double tm;
-			if (medium_event(sc, sc.media[mi], ray, a, 0.001, tmax, u01, tm)) { tmax = tm; medium_hit = mi; }
+			if (medium_event(sc, sc.media[mi], ray, a, inv_a, 0.001, tmax, u01, tm)) { tmax = tm; medium_hit = mi; }
 		}
 	}
-	Hit h = trace_closest<kCount>(sc, ray, 0.001, tmax, &pc.node_visits);
+	return true;
+}
+
+// The rest of the level: miss -> background; hit -> emitted + scatter.  `h` is the closest surface hit found with
+// tmax = the medium candidate.  Returns true when the path is finished; st.L then holds the sample colour.
+__device__ __forceinline__ bool segment_shade(const DeviceScene& sc, const DCamera& cam, const uint8_t* __restrict__ perm, PathState& st,
+                                              PathCounters& pc, const Hit& h, double tmax, int medium_hit) {
+	Ray& ray = st.ray;
 	f3 d_in = mk3((float)ray.dx, (float)ray.dy, (float)ray.dz);
 	if (h.ref == kNoHit && medium_hit < 0) {  // sample_background, camera.rs:228-233
 		f3 bg = background(sc, cam, d_in, pc.tex_fetches);
@@ -338,8 +369,8 @@ __device__ __forceinline__ bool path_step(const DeviceScene& sc, const DCamera& 
 			DSphere sp = load_sphere(sc.spheres, index);
 			double cx = sp.cx, cy = sp.cy, cz = sp.cz, rad = sp.r;
 			if (rad < 0.0) { double4 p = sc.sph_path[index]; cx += ray.time * p.x; cy += ray.time * p.y; cz += ray.time * p.z; rad = -rad; }
-			double inv_r = 1.0 / rad;
-			n_out = mk3((float)((s.px - cx) * inv_r), (float)((s.py - cy) * inv_r), (float)((s.pz - cz) * inv_r));  // sphere.rs:91
+			const float inv_r = 1.0f / (float)rad;  // outward_normal = (p - c) / r (sphere.rs:91), difference in f64, quotient in f32
+			n_out = mk3((float)(s.px - cx) * inv_r, (float)(s.py - cy) * inv_r, (float)(s.pz - cz) * inv_r);
 			s.is_sphere = true; s.u = 0.f; s.v = 0.f;
 			s.material = __ldg(sc.sph_aux + index).x;
 		} else {
@@ -367,6 +398,17 @@ __device__ __forceinline__ bool path_step(const DeviceScene& sc, const DCamera& 
 	ray.dx = (double)d_out.x; ray.dy = (double)d_out.y; ray.dz = (double)d_out.z;
 	++st.bounce;
 	return false;
+}
+
+// One whole level, run to completion (adaptive kernel and the per-path hooks).
+template <bool kCount>
+__device__ __forceinline__ bool path_step(const DeviceScene& sc, const DCamera& cam, const uint8_t* __restrict__ perm, PathState& st,
+                                          PathCounters& pc) {
+	double tmax;
+	int medium_hit;
+	if (!segment_begin(sc, cam, st, pc, tmax, medium_hit)) return true;
+	Hit h = trace_closest<kCount>(sc, st.ray, 0.001, tmax, &pc.node_visits);
+	return segment_shade(sc, cam, perm, st, pc, h, tmax, medium_hit);
 }
 
 }  // namespace gs

@@ -11,38 +11,32 @@
 //   stop-test semantics (Q3-Q5): one warp per pixel, a batch's samples spread over the lanes.
 // Grids are sized to SM count x resident CTAs (persistent), never to the image.
 #include "gs_internal.h"
-#include "gs_shade.cuh"
+#include "gs_kernel_util.cuh"
 
 namespace gs {
 
-constexpr int kBlock = 128;
-constexpr unsigned kFull = 0xffffffffu;
-
-__device__ __forceinline__ void red_add_v4(float4* addr, float a, float b, float c, float d) {
-	asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-
-__device__ __forceinline__ void load_perm(uint8_t* s_perm, const uint8_t* g_perm) {
-	for (int i = threadIdx.x; i < 256; i += blockDim.x) s_perm[i] = g_perm ? g_perm[i] : (uint8_t)i;
-	__syncthreads();
-}
-
-__device__ __forceinline__ void flush_stats(unsigned long long* stats, const PathCounters& pc, unsigned paths) {
-	unsigned r = pc.rays, t = pc.tex_fetches, n = pc.node_visits, p = paths;
-#pragma unroll
-	for (int o = 16; o > 0; o >>= 1) {
-		r += __shfl_xor_sync(kFull, r, o); t += __shfl_xor_sync(kFull, t, o);
-		n += __shfl_xor_sync(kFull, n, o); p += __shfl_xor_sync(kFull, p, o);
-	}
-	// per-thread counters are 32-bit; one warp handles far fewer than 2^32 rays per launch
-	if ((threadIdx.x & 31) == 0) {
-		atomicAdd(stats + 0, (unsigned long long)r); atomicAdd(stats + 1, (unsigned long long)p);
-		atomicAdd(stats + 2, (unsigned long long)t); atomicAdd(stats + 3, (unsigned long long)n);
-	}
-}
+// Lane states of the megakernel.  A lane is a path; the warp alternates between two phases:
+//   phase A (shade / regenerate / set up): lanes whose ray has finished are shaded, finished paths are
+//            accumulated and replaced by the next (pixel, sample) item, and every lane with a fresh ray
+//            evaluates the media and initialises its traversal;
+//   phase B (traverse): all lanes with an unfinished ray walk the BVH.  The phase ends as soon as kMinShade
+//            lanes have finished (or nobody is traversing): the others KEEP their traversal state (node, sp,
+//            closest hit, stack) and continue in the next phase B.
+enum LaneState : int { kDead = 0, kTraverse = 1, kShade = 2, kSetup = 3 };
+// Tuning knobs (overridable with -D for the A/B sweeps of scripts/gpu_sweep.sh; defaults = the measured best).
+#ifndef GS_MIN_SHADE
+#define GS_MIN_SHADE 32   // leave phase B once this many lanes wait for shading (32 = run every ray to completion)
+#endif
+#ifndef GS_MIN_BLOCKS
+#define GS_MIN_BLOCKS 4   // __launch_bounds__ min CTAs per SM (register cap = 65536 / (128 * GS_MIN_BLOCKS))
+#endif
+#ifndef GS_TRAV_VOTE
+#define GS_TRAV_VOTE 0    // 0 = while-while rounds, 1 = per-iteration node/leaf vote
+#endif
+constexpr int kMinShade = GS_MIN_SHADE;
 
 template <bool kCount>
-__global__ void __launch_bounds__(kBlock) render_fixed_kernel(const __grid_constant__ RenderParams P) {
+__global__ void __launch_bounds__(kBlock, GS_MIN_BLOCKS) render_fixed_kernel(const __grid_constant__ RenderParams P) {
 	__shared__ uint8_t s_perm[256];
 	load_perm(s_perm, P.sc.perlin_perm);
 	const unsigned lane = threadIdx.x & 31u;
@@ -50,15 +44,35 @@ __global__ void __launch_bounds__(kBlock) render_fixed_kernel(const __grid_const
 	PathCounters pc = {0u, 0u, 0u};
 	unsigned paths = 0;
 	PathState st;
-	bool alive = false;
+	int state = kDead;
+	TravState tv;
+	tv.node = kStackSentinel; tv.sp = 0;
+	double seg_tmax = 0.0;
+	int seg_medium = -1;
+	int stack[kMaxStack];
 	float ar = 0.f, ag = 0.f, ab = 0.f, an = 0.f;
 	uint32_t cur_pixel = 0xffffffffu;
 	unsigned long long warp_next = 0, warp_end = 0;
 	bool exhausted = false;
 
+	auto finish_path = [&]() {  // pixel_color += sample_color, camera.rs:141
+		if (st.pixel != cur_pixel) {
+			if (cur_pixel != 0xffffffffu) red_add_v4(P.accum + cur_pixel, ar, ag, ab, an);
+			cur_pixel = st.pixel; ar = ag = ab = an = 0.f;
+		}
+		ar += st.L.x; ag += st.L.y; ab += st.L.z; an += 1.f;
+		state = kDead;
+	};
+
 	for (;;) {
-		const unsigned dead = __ballot_sync(kFull, !alive);
-		if (dead) {
+		// ---- phase A1: shade the lanes whose traversal finished --------------------------------------
+		if (state == kShade) {
+			if (segment_shade(P.sc, P.cam, s_perm, st, pc, tv.best, seg_tmax, seg_medium)) finish_path();
+			else state = kSetup;
+		}
+		// ---- phase A2: dead lanes take the next (pixel, sample) items ------------------------------------
+		const unsigned dead = __ballot_sync(kFull, state == kDead);
+		if (dead && !(exhausted && warp_next >= warp_end)) {
 			if (warp_next >= warp_end && !exhausted) {
 				unsigned long long base = 0;
 				if (lane == 0) base = atomicAdd(P.work_counter, (unsigned long long)P.chunk);
@@ -67,34 +81,74 @@ __global__ void __launch_bounds__(kBlock) render_fixed_kernel(const __grid_const
 				else { warp_next = base; warp_end = min(base + (unsigned long long)P.chunk, P.total_items); }
 			}
 			const unsigned long long avail = warp_end - warp_next;
-			if (!alive) {
+			if (state == kDead) {
 				const unsigned rank = __popc(dead & lt_mask);
 				if (rank < avail) {
 					const unsigned long long item = warp_next + rank;
 					const uint32_t pixel = (uint32_t)(item / P.sample_count);
 					const uint32_t sample = (uint32_t)(item % P.sample_count) + P.sample_begin;
 					path_begin(st, P.cam, P.seed, pixel, sample);
-					alive = true;
+					state = kSetup;
 					++paths;
 				}
 			}
 			const unsigned long long need = (unsigned long long)__popc(dead);
 			warp_next += need < avail ? need : avail;
 		}
-		if (!__any_sync(kFull, alive)) {
-			if (exhausted) break;
+		// ---- phase A3: depth test, media, traversal set-up for every fresh ray ----------------------------
+		if (state == kSetup) {
+			if (segment_begin(P.sc, P.cam, st, pc, seg_tmax, seg_medium)) {
+				trav_init(P.sc, tv, stack, seg_tmax);
+				state = kTraverse;
+			} else finish_path();  // depth exhausted; the lane picks up new work in the next phase A
+		}
+		const unsigned trav0 = __ballot_sync(kFull, state == kTraverse);
+		if (trav0 == 0u) {
+			if (exhausted && warp_next >= warp_end && __ballot_sync(kFull, state != kDead) == 0u) break;
 			continue;
 		}
-		if (alive) {
-			if (path_step<kCount>(P.sc, P.cam, s_perm, st, pc)) {
-				if (st.pixel != cur_pixel) {
-					if (cur_pixel != 0xffffffffu) red_add_v4(P.accum + cur_pixel, ar, ag, ab, an);
-					cur_pixel = st.pixel; ar = ag = ab = an = 0.f;
+		// ---- phase B: traverse until enough lanes have finished their ray ---------------------------------
+		RayConsts rc;
+		if (state == kTraverse) rc = ray_consts(st.ray, tv.best.t);
+#if GS_TRAV_VOTE
+		// Per-iteration vote: if at least as many lanes sit on an internal node as on a leaf, the node lanes take
+		// two node steps, otherwise the leaf lanes intersect their leaf; the others wait.
+		for (;;) {
+			const bool trav = state == kTraverse;
+			const bool at_node = trav && tv.node >= 0;
+			const unsigned m_node = __ballot_sync(kFull, at_node);
+			const unsigned m_leaf = __ballot_sync(kFull, trav && !at_node);
+			const unsigned m_shade = __ballot_sync(kFull, state == kShade);
+			if ((m_node | m_leaf) == 0u || __popc(m_shade) >= kMinShade) break;
+			if (__popc(m_node) >= __popc(m_leaf)) {
+				if (at_node) {
+					node_step<kCount>(P.sc, rc, tv, stack, &pc.node_visits);
+					if (tv.node >= 0) node_step<kCount>(P.sc, rc, tv, stack, &pc.node_visits);
 				}
-				ar += st.L.x; ag += st.L.y; ab += st.L.z; an += 1.f;  // pixel_color += sample_color, camera.rs:141
-				alive = false;
+			} else if (trav && !at_node) {
+				leaf_step(P.sc, st.ray, rc, 0.001, tv, stack);
+			}
+			if (trav && tv.node == kStackSentinel) state = kShade;
+		}
+#elif GS_MIN_SHADE >= 32
+		// Every lane runs its ray to completion (classic while-while); measured best on B200.
+		if (state == kTraverse) {
+			while (tv.node != kStackSentinel) trav_round<kCount>(P.sc, st.ray, rc, 0.001, tv, stack, &pc.node_visits);
+			state = kShade;
+		}
+#else
+		// Resumable while-while rounds: leave as soon as kMinShade lanes have finished their ray.
+		for (;;) {
+			const bool trav = state == kTraverse;
+			const unsigned m_trav = __ballot_sync(kFull, trav);
+			const unsigned m_shade = __ballot_sync(kFull, state == kShade);
+			if (m_trav == 0u || __popc(m_shade) >= kMinShade) break;
+			if (trav) {
+				trav_round<kCount>(P.sc, st.ray, rc, 0.001, tv, stack, &pc.node_visits);
+				if (tv.node == kStackSentinel) state = kShade;
 			}
 		}
+#endif
 	}
 	if (cur_pixel != 0xffffffffu) red_add_v4(P.accum + cur_pixel, ar, ag, ab, an);
 	flush_stats(P.stats, pc, paths);

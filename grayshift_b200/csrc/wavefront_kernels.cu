@@ -1,0 +1,215 @@
+// grayshift_b200/csrc/wavefront_kernels.cu -- the wavefront form of the fixed-count renderer (sm_100a).
+//
+// Why it exists (ncu on the megakernel, profiles/r01_v0_*, r01_v1_*): 107 KB of SASS against a 32 KB instruction
+// cache (42 % of warp stalls were "no instruction"), 124-128 registers (16 warps/SM), and 10 of 32 lanes active per
+// instruction because one kernel interleaves traversal, five materials, four textures, media and ray generation.
+// Splitting along the reference's own call structure gives three small kernels per wave over a pool of in-flight
+// paths kept in HBM as a structure of arrays (PathPool, 112 B per path, all accesses 128-bit and coalesced):
+//
+//   wf_generate_kernel  Camera::get_ray (camera.rs:204-226) for every free slot: path regeneration
+//   wf_traverse_kernel  ConstantMedium::hit + BVHNode/AABB/Sphere/Quad::hit (world.hit, camera.rs:177): persistent
+//                       warps that fetch the next ray the moment a lane finishes its ray (dynamic ray fetch)
+//   wf_shade_kernel     emitted + scatter + value_at + sample_background (camera.rs:178-201), accumulation of
+//                       finished paths (camera.rs:141), and the free list for the next generate
+//
+// A slot's path survives from wave to wave; the host launches waves until every (pixel, sample) item has been
+// started and the pool is empty.  Random numbers are the same Philox streams as in the megakernel and the oracle
+// (counter = pixel, sample, draw), so the two pipelines render the same image up to fp32 summation order.
+#include "gs_internal.h"
+#include "gs_kernel_util.cuh"
+
+namespace gs {
+
+constexpr int kRefill = 8;  // traverse: fetch new rays once this many lanes of a warp are idle
+
+__device__ __forceinline__ unsigned lanemask_lt() { return (1u << (threadIdx.x & 31u)) - 1u; }
+
+// ---- generate ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) wf_generate_kernel(const __grid_constant__ WavefrontParams P, const int first_wave) {
+	const unsigned i = blockIdx.x * kBlock + threadIdx.x;
+	const unsigned lane = threadIdx.x & 31u;
+	const unsigned n_todo = first_wave ? (unsigned)P.pool.n : P.ctr->n_free;
+	const bool has = i < n_todo;
+	const int slot = has ? (first_wave ? (int)i : P.free_list[i]) : -1;
+	const unsigned m = __ballot_sync(kFull, has);
+	if (m == 0u) return;
+	unsigned long long base = 0;
+	const int leader = __ffs(m) - 1;
+	if ((int)lane == leader) base = atomicAdd(&P.ctr->next_item, (unsigned long long)__popc(m));
+	base = __shfl_sync(kFull, base, leader);
+	const unsigned long long item = base + __popc(m & lanemask_lt());
+	const bool start = has && item < P.total_items;
+	if (start) {
+		PathState st;
+		const uint32_t pixel = (uint32_t)(item / P.sample_count);
+		const uint32_t sample = (uint32_t)(item % P.sample_count) + P.sample_begin;
+		path_begin(st, P.cam, P.seed, pixel, sample);
+		P.pool.org[slot] = make_double4(st.ray.ox, st.ray.oy, st.ray.oz, st.ray.time);
+		P.pool.dir[slot] = make_double4(st.ray.dx, st.ray.dy, st.ray.dz, 0.0);
+		P.pool.thr[slot] = make_float4(1.f, 1.f, 1.f, 0.f);
+		P.pool.rad[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+		P.pool.ids[slot] = make_uint4(pixel, sample, st.rng.draw, 0u | kSlotActive);
+	} else if (has && first_wave) {
+		P.pool.ids[slot] = make_uint4(0u, 0u, 0u, 0u);
+	}
+	const unsigned ms = __ballot_sync(kFull, start);
+	if (ms && (int)lane == leader) {
+		atomicAdd(&P.ctr->n_live, __popc(ms));
+		atomicAdd(P.stats + 1, (unsigned long long)__popc(ms));  // paths started
+	}
+}
+
+// ---- traverse ------------------------------------------------------------------------------------------
+template <bool kCount>
+__global__ void __launch_bounds__(kBlock) wf_traverse_kernel(const __grid_constant__ WavefrontParams P) {
+	const unsigned lane = threadIdx.x & 31u;
+	const unsigned lt = lanemask_lt();
+	const unsigned n = (unsigned)P.pool.n;
+	int slot = -1;
+	Ray ray;
+	TravState tv;
+	RayConsts rc;
+	int medium = -1;
+	int stack[kMaxStack];
+	PathCounters pc = {0u, 0u, 0u};
+	bool drained = false;
+	tv.node = kStackSentinel; tv.sp = 0;
+
+	for (;;) {
+		const unsigned idle = __ballot_sync(kFull, slot < 0);
+		if (!drained && (__popc(idle) >= kRefill)) {
+			unsigned base = 0;
+			if (lane == 0) base = atomicAdd(&P.ctr->next_ray, (unsigned)__popc(idle));
+			base = __shfl_sync(kFull, base, 0);
+			if (base + (unsigned)__popc(idle) >= n) drained = true;
+			if (slot < 0) {
+				const unsigned s = base + __popc(idle & lt);
+				if (s < n) {
+					const uint4 id = P.pool.ids[s];
+					if (id.w & kSlotActive) {
+						const double4 o = P.pool.org[s], d = P.pool.dir[s];
+						ray.ox = o.x; ray.oy = o.y; ray.oz = o.z; ray.time = o.w;
+						ray.dx = d.x; ray.dy = d.y; ray.dz = d.z;
+						// media first (volume.rs:32-63): the closest medium event bounds the surface search
+						double tmax = 1.7976931348623157e308;
+						medium = -1;
+						++pc.rays;
+						if (P.sc.n_media > 0) {
+							const double a = ray.dx * ray.dx + ray.dy * ray.dy + ray.dz * ray.dz;
+							const double inv_a = 1.0 / a;
+							const uint32_t bounce = id.w & 0xffffu;
+							uint4 blk = make_uint4(0u, 0u, 0u, 0u);
+							for (int mi = 0; mi < P.sc.n_media; ++mi) {
+								if ((mi & 3) == 0)
+									blk = philox4x32_10(id.x, id.y, bounce * 64u + (uint32_t)(mi >> 2), 1u, (uint32_t)P.seed, (uint32_t)(P.seed >> 32));
+								const uint32_t w = (mi & 3) == 0 ? blk.x : ((mi & 3) == 1 ? blk.y : ((mi & 3) == 2 ? blk.z : blk.w));
+								const float u01 = (float)(w >> 8) * (1.0f / 16777216.0f);
+								double tm;
+								if (medium_event(P.sc, P.sc.media[mi], ray, a, inv_a, 0.001, tmax, u01, tm)) { tmax = tm; medium = mi; }
+							}
+						}
+						trav_init(P.sc, tv, stack, tmax);
+						rc = ray_consts(ray, tmax);
+						slot = (int)s;
+					}
+				}
+			}
+		}
+		if (__ballot_sync(kFull, slot >= 0) == 0u) {
+			if (drained) break;
+			continue;
+		}
+		if (slot >= 0) {
+			trav_round<kCount>(P.sc, ray, rc, 0.001, tv, stack, &pc.node_visits);
+			if (tv.node == kStackSentinel) {
+				// closest event: surface hit (ref), else medium event (t = the medium's candidate), else miss
+				reinterpret_cast<double*>(P.pool.dir + slot)[3] = tv.best.t;
+				P.pool.hit[slot] = make_uint4(tv.best.ref, (unsigned)medium, __float_as_uint((float)tv.best.u), __float_as_uint((float)tv.best.v));
+				slot = -1;
+			}
+		}
+	}
+	flush_stats(P.stats, pc, 0u);
+}
+
+// ---- shade -----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) wf_shade_kernel(const __grid_constant__ WavefrontParams P) {
+	__shared__ uint8_t s_perm[256];
+	load_perm(s_perm, P.sc.perlin_perm);
+	const unsigned s = blockIdx.x * kBlock + threadIdx.x;
+	const unsigned lane = threadIdx.x & 31u;
+	PathCounters pc = {0u, 0u, 0u};
+	bool terminated = false;
+	uint4 id = make_uint4(0u, 0u, 0u, 0u);
+	if (s < (unsigned)P.pool.n) id = P.pool.ids[s];
+	if (id.w & kSlotActive) {
+		PathState st;
+		const double4 o = P.pool.org[s], d = P.pool.dir[s];
+		const float4 thr = P.pool.thr[s], rad = P.pool.rad[s];
+		const uint4 hw = P.pool.hit[s];
+		st.ray.ox = o.x; st.ray.oy = o.y; st.ray.oz = o.z; st.ray.time = o.w;
+		st.ray.dx = d.x; st.ray.dy = d.y; st.ray.dz = d.z;
+		st.T = mk3(thr.x, thr.y, thr.z);
+		st.L = mk3(rad.x, rad.y, rad.z);
+		st.pixel = id.x;
+		st.bounce = id.w & 0xffffu;
+		st.rng.pixel = id.x; st.rng.sample = id.y; st.rng.draw = id.z;
+		st.rng.k0 = (uint32_t)P.seed; st.rng.k1 = (uint32_t)(P.seed >> 32);
+		// mid-block: rebuild the Philox block the next draws come from (draw k = word k&3 of block k>>2)
+		if (id.z & 3u) st.rng.buf = philox4x32_10(id.x, id.y, id.z >> 2, 0u, st.rng.k0, st.rng.k1);
+		Hit h;
+		h.t = d.w; h.ref = hw.x; h.u = (double)__uint_as_float(hw.z); h.v = (double)__uint_as_float(hw.w);
+		bool finished = segment_shade(P.sc, P.cam, s_perm, st, pc, h, d.w, (int)hw.y);
+		if (!finished && st.bounce >= P.cam.max_depth) finished = true;  // the next level returns ZERO (camera.rs:175)
+		if (finished) {
+			red_add_v4(P.accum + st.pixel, st.L.x, st.L.y, st.L.z, 1.0f);  // pixel_color += sample_color (camera.rs:141)
+			P.pool.ids[s] = make_uint4(id.x, id.y, st.rng.draw, 0u);
+			terminated = true;
+		} else {
+			P.pool.org[s] = make_double4(st.ray.ox, st.ray.oy, st.ray.oz, st.ray.time);
+			P.pool.dir[s] = make_double4(st.ray.dx, st.ray.dy, st.ray.dz, 0.0);
+			P.pool.thr[s] = make_float4(st.T.x, st.T.y, st.T.z, 0.f);
+			P.pool.rad[s] = make_float4(st.L.x, st.L.y, st.L.z, 0.f);
+			P.pool.ids[s] = make_uint4(id.x, id.y, st.rng.draw, st.bounce | kSlotActive);
+		}
+	}
+	// released slots -> free list (warp-aggregated: one atomic per warp)
+	const unsigned m = __ballot_sync(kFull, terminated);
+	if (m) {
+		unsigned base = 0;
+		const int leader = __ffs(m) - 1;
+		if ((int)lane == leader) {
+			base = atomicAdd(&P.ctr->n_free, (unsigned)__popc(m));
+			atomicSub(&P.ctr->n_live, __popc(m));
+		}
+		base = __shfl_sync(kFull, base, leader);
+		if (terminated) P.free_list[base + __popc(m & lanemask_lt())] = (int)s;
+	}
+	flush_stats(P.stats, pc, 0u);
+}
+
+// ---- launch wrappers ---------------------------------------------------------------------------------------
+cudaError_t launch_wf_generate(const WavefrontParams& p, bool first_wave, cudaStream_t stream) {
+	wf_generate_kernel<<<(p.pool.n + kBlock - 1) / kBlock, kBlock, 0, stream>>>(p, first_wave ? 1 : 0);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_wf_traverse(const WavefrontParams& p, int sm_count, bool count_nodes, cudaStream_t stream) {
+	int per_sm = 0;
+	if (count_nodes) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_traverse_kernel<true>, kBlock, 0);
+	else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_traverse_kernel<false>, kBlock, 0);
+	if (per_sm < 1) per_sm = 1;
+	long long grid = (long long)sm_count * per_sm;  // persistent: SMs x resident CTAs
+	const long long needed = (p.pool.n + kBlock - 1) / kBlock;
+	if (needed < grid) grid = needed;
+	if (count_nodes) wf_traverse_kernel<true><<<(unsigned)grid, kBlock, 0, stream>>>(p);
+	else wf_traverse_kernel<false><<<(unsigned)grid, kBlock, 0, stream>>>(p);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_wf_shade(const WavefrontParams& p, cudaStream_t stream) {
+	wf_shade_kernel<<<(p.pool.n + kBlock - 1) / kBlock, kBlock, 0, stream>>>(p);
+	return cudaGetLastError();
+}
+
+}  // namespace gs
