@@ -28,6 +28,15 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# stdout carries exactly ONE JSON line.  Libraries (NCCL prints its version banner there) get stderr instead.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 FULL_SPP = {"c1": 100, "c2": 1000, "c3": 1000, "c4": 10000, "c5": 4096}
 WORKLOAD = {
     "c1": "Book-1 random spheres (config 1), 400x225, max_depth 50",
@@ -136,7 +145,7 @@ def run_reference(args):
                              "sample": f"{args.config} full resolution {s.width}x{s.height}, {spp} spp per step, {args.steps} steps; C++ port of the Rust "
                                        f"reference (the Rust itself cannot be built: no cargo/rustc), {cores} threads"},
             "e2e": {"value": value, "unit": "paths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -148,6 +157,7 @@ def main():
     ap.add_argument("--impl", default="grayshift_b200")
     ap.add_argument("--config", default="c4", choices=sorted(WORKLOAD))
     ap.add_argument("--spp-per-step", type=int, default=0)
+    ap.add_argument("--max-leaf", type=int, default=0, help="BVH leaf size limit handed to the host builder (0 = its default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--pipeline", default="megakernel", choices=["megakernel", "wavefront"],
@@ -176,7 +186,7 @@ def main():
     spp_step = args.spp_per_step or {"c1": 100, "c2": 200, "c3": 250, "c4": 500, "c5": 16}[args.config]
     host = gs.HostScene.build(args.config, spp=spp_step)
     t0 = time.perf_counter()
-    host.flatten()
+    host.flatten(max_leaf_size=args.max_leaf)
     flatten_s = time.perf_counter() - t0
     scene = gs.DeviceScene(host, device=local_rank)
     scene.set_option("wavefront", 1 if args.pipeline == "wavefront" else 0)
@@ -267,11 +277,12 @@ def main():
             "config": {"workload": WORKLOAD[args.config], "samples_per_pixel_per_step": spp_step, "full_config_spp": FULL_SPP[args.config],
                        "scene_seed": 1, "render_seed": 1, "l2": "flushed between timed steps (256 MiB write); scene working set itself is L2-resident",
                        "parallelism": f"spp-split x{world}, NCCL reduce of the fp32 accumulator each step" if world > 1 else "single GPU",
-                       "bvh": "binned SAH, binary, <=4 prims/leaf", "pipeline": args.pipeline, "host_flatten_s": round(flatten_s, 3)},
+                       "bvh": f"binned SAH, binary, <={args.max_leaf or 4} prims/leaf", "pipeline": args.pipeline, "host_flatten_s": round(flatten_s, 3)},
             "e2e": {"value": e2e_value, "unit": "paths/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "what": "gs_scene_create + gs_render_accumulate + reduce + gs_resolve to host, per step"},
             "gpu_launches": int(st.kernel_launches) * world,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": k.get("ncu_dram_bytes_per_launch") if args.pipeline == "megakernel" else None,
+                         "traffic_note": k.get("ncu_dram_note"),
                          "peak_source": peak_src, "kernel": "render_fixed_kernel" if args.pipeline == "megakernel" else "wf_traverse_kernel + wf_shade_kernel + wf_generate_kernel",
                          "algorithmic_bytes_per_ray": k["bytes_per_ray"],
                          "note": "algorithmic bytes = reference-semantics box/prim/texel counts x 32/32/16 B; the scene is L1/L2 resident, so this is a "
@@ -280,7 +291,7 @@ def main():
         }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(args.config)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
