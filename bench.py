@@ -277,7 +277,7 @@ def main():
             "config": {"workload": WORKLOAD[args.config], "samples_per_pixel_per_step": spp_step, "full_config_spp": FULL_SPP[args.config],
                        "scene_seed": 1, "render_seed": 1, "l2": "flushed between timed steps (256 MiB write); scene working set itself is L2-resident",
                        "parallelism": f"spp-split x{world}, NCCL reduce of the fp32 accumulator each step" if world > 1 else "single GPU",
-                       "bvh": f"binned SAH, binary, <={args.max_leaf or 4} prims/leaf", "pipeline": args.pipeline, "host_flatten_s": round(flatten_s, 3)},
+                       "bvh": f"binned SAH, binary, <={args.max_leaf or 1} prims/leaf", "pipeline": args.pipeline, "host_flatten_s": round(flatten_s, 3)},
             "e2e": {"value": e2e_value, "unit": "paths/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "what": "gs_scene_create + gs_render_accumulate + reduce + gs_resolve to host, per step"},
             "gpu_launches": int(st.kernel_launches) * world,

@@ -388,6 +388,11 @@ int gs_scene_create(const gs_scene_desc* d, int device, gs_scene** out) {
 				}
 				if (first >= (1u << 27) - 1u) return fail(GS_ERR_UNSUPPORTED, "too many primitive references");
 				s->h_leaf_code[n] = leaf_code(first, (uint32_t)nd.ref_count);
+				if (nd.ref_count == 1) {
+					// single-primitive leaf: put (kind << 26 | index) into the link itself, count field 0
+					const uint32_t r = refs.back(), kind = r >> 30, idx = r & kRefIndexMask;
+					if (idx < (1u << 26)) s->h_leaf_code[n] = leaf_code((kind << 26) | idx, 0u);
+				}
 			} else { stack.push_back(nd.right); stack.push_back(nd.left); }
 		}
 	}

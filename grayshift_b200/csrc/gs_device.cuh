@@ -30,7 +30,8 @@ struct __align__(16) DNode {
 	float4 z01;  // c0.min.z, c0.max.z, c1.min.z, c1.max.z
 	int4 link;   // child0, child1 (>= 0 internal node index; < 0 leaf code), unused, unused
 };
-// leaf code: -1 - ((first_ref << 4) | count), count <= 15
+// leaf code: -1 - ((first_ref << 4) | count), 1 <= count <= 15; count == 0 marks a single-primitive leaf whose
+// reference (kind << 26 | index) sits in the first_ref field itself
 __host__ __device__ inline int leaf_code(uint32_t first, uint32_t count) { return -1 - (int)((first << 4) | count); }
 // Negative (so the inner "internal node" loop stops on it) and not a valid leaf code: it would need
 // first_ref = 2^27 - 1 with count 15, which gs_scene_create rejects.
@@ -275,9 +276,13 @@ __device__ __forceinline__ void node_step(const DeviceScene& sc, const RayConsts
 __device__ __forceinline__ void leaf_step(const DeviceScene& sc, const Ray& r, RayConsts& rc, double tmin, TravState& tv, int* stack) {
 	Hit& best = tv.best;
 	const uint32_t code = (uint32_t)(-1 - tv.node);
-	const uint32_t first = code >> 4, count = code & 15u;
+	uint32_t first = code >> 4, count = code & 15u;
+	// count == 0: a single-primitive leaf whose reference is stored in the link itself (kind << 26 | index):
+	// no dependent load from `refs` between the node and the primitive
+	const bool direct = count == 0u;
+	if (direct) count = 1u;
 	for (uint32_t k = 0; k < count; ++k) {
-		const uint32_t ref = __ldg(sc.refs + first + k);
+		const uint32_t ref = direct ? (((first >> 26) << kRefKindShift) | (first & ((1u << 26) - 1u))) : __ldg(sc.refs + first + k);
 		const uint32_t index = ref & kRefIndexMask;
 		if ((ref >> kRefKindShift) == 0u) {
 			const DSphere s = load_sphere(sc.spheres, index);
