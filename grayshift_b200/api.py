@@ -130,6 +130,15 @@ class DeviceScene:
                                        C.c_void_p(stream)))
         return rgb.reshape(self.height, self.width, 3), counts.reshape(self.height, self.width)
 
+    def resolve_rgb8(self, d_accum_ptr, stream=0):
+        """Device output stage: /count + write_color's transfer (src/color.rs:8-26) -> uint8 [H,W,3] on the host."""
+        n = self.width * self.height
+        rgb8 = np.empty((n, 3), dtype=np.uint8)
+        counts = np.empty(n, dtype=np.uint32)
+        ffi.check(self._lib.gs_resolve_rgb8(self._h, C.c_void_p(d_accum_ptr), self.width, self.height, rgb8.ctypes.data, counts.ctypes.data,
+                                            C.c_void_p(stream)))
+        return rgb8.reshape(self.height, self.width, 3), counts.reshape(self.height, self.width)
+
     def stats(self):
         st = ffi.gs_stats()
         ffi.check(self._lib.gs_stats_read(self._h, C.byref(st)))

@@ -69,6 +69,8 @@ struct gs_scene {
 	DevBuf<DQuad> quads;
 	DevBuf<int2> quad_aux;
 	DevBuf<int> quad_order;
+	DevBuf<DTriangle> tris;
+	DevBuf<int2> tri_aux;
 	DevBuf<DSphere> bnd_spheres;
 	DevBuf<double4> bnd_sph_path;
 	DevBuf<DQuad> bnd_quads;
@@ -90,6 +92,7 @@ struct gs_scene {
 	int next_counter = 0;
 	uint64_t launches = 0;
 	bool count_nodes = false;
+	bool has_triangles = false;  // selects the kernel variants that carry the triangle branch
 	uint64_t h2d_bytes = 0;
 
 	// wavefront pipeline: path pool (structure of arrays) + counters.  Off by default: measured against the
@@ -110,7 +113,7 @@ struct gs_scene {
 		free_list.release(); wave_ctr.release();
 		if (h_wave_ctr) cudaFreeHost(h_wave_ctr);
 		nodes.release(); refs.release(); spheres.release(); sph_path.release(); sph_aux.release(); quads.release(); quad_aux.release();
-		quad_order.release(); bnd_spheres.release(); bnd_sph_path.release(); bnd_quads.release(); media.release(); materials.release();
+		quad_order.release(); tris.release(); tri_aux.release(); bnd_spheres.release(); bnd_sph_path.release(); bnd_quads.release(); media.release(); materials.release();
 		textures.release(); images.release(); perm.release(); accum.release(); out_rgb.release(); out_counts.release(); counters.release();
 		stats.release();
 	}
@@ -146,11 +149,21 @@ DQuad make_dquad(const gs_quad& g) {
 	return d;
 }
 
+// Triangle::new (triangle.rs:20-28) keeps a, b, c; the two edges hit() recomputes per call are stored instead.
+DTriangle make_dtriangle(const gs_triangle& t) {
+	DTriangle d;
+	d.ax = t.a[0]; d.ay = t.a[1]; d.az = t.a[2]; d.pad0 = 0.0;
+	d.e1x = t.c[0] - t.a[0]; d.e1y = t.c[1] - t.a[1]; d.e1z = t.c[2] - t.a[2]; d.pad1 = 0.0;  // edge_1 = c - a
+	d.e2x = t.b[0] - t.a[0]; d.e2y = t.b[1] - t.a[1]; d.e2z = t.b[2] - t.a[2]; d.pad2 = 0.0;  // edge_2 = b - a
+	return d;
+}
+
 int validate(const gs_scene_desc* d) {
 	if (!d) return fail(GS_ERR_INVALID, "null scene description");
 	if (d->abi_version != GS_ABI_VERSION) return fail(GS_ERR_INVALID, "abi_version mismatch");
-	if (d->n_spheres + d->n_quads == 0) return fail(GS_ERR_INVALID, "empty scene (the reference recurses forever on an empty list, BVH.rs:18-65)");
-	if (d->n_spheres >= (1u << 30) || d->n_quads >= (1u << 30)) return fail(GS_ERR_UNSUPPORTED, "too many primitives");
+	if (d->n_spheres + d->n_quads + d->n_triangles == 0) return fail(GS_ERR_INVALID, "empty scene (the reference recurses forever on an empty list, BVH.rs:18-65)");
+	if (d->n_spheres >= (1u << 30) || d->n_quads >= (1u << 30) || d->n_triangles >= (1u << 30)) return fail(GS_ERR_UNSUPPORTED, "too many primitives");
+	if (d->n_triangles && !d->triangles) return fail(GS_ERR_INVALID, "null triangle array");
 	if (d->n_nodes == 0 || !d->nodes) return fail(GS_ERR_INVALID, "no BVH nodes");
 	if (d->n_materials == 0 || !d->materials) return fail(GS_ERR_INVALID, "no materials");
 	auto bad_mat = [&](int m) { return m < 0 || (size_t)m >= d->n_materials; };
@@ -163,6 +176,11 @@ int validate(const gs_scene_desc* d) {
 		const gs_quad& q = d->quads[i];
 		if (!finite3(q.q) || !finite3(q.u) || !finite3(q.v)) return fail(GS_ERR_INVALID, "quad " + std::to_string(i) + ": non-finite");
 		if (bad_mat(q.material)) return fail(GS_ERR_INVALID, "quad " + std::to_string(i) + ": bad material index");
+	}
+	for (size_t i = 0; i < d->n_triangles; ++i) {
+		const gs_triangle& t = d->triangles[i];
+		if (!finite3(t.a) || !finite3(t.b) || !finite3(t.c)) return fail(GS_ERR_INVALID, "triangle " + std::to_string(i) + ": non-finite");
+		if (bad_mat(t.material)) return fail(GS_ERR_INVALID, "triangle " + std::to_string(i) + ": bad material index");
 	}
 	for (size_t i = 0; i < d->n_boundary_spheres; ++i)
 		if (!finite3(d->boundary_spheres[i].center) || !std::isfinite(d->boundary_spheres[i].radius)) return fail(GS_ERR_INVALID, "boundary sphere: non-finite");
@@ -209,7 +227,8 @@ int validate(const gs_scene_desc* d) {
 	}
 	for (size_t i = 0; i < d->n_prim_refs; ++i) {
 		uint32_t r = d->prim_refs[i], kind = r >> 30, idx = r & kRefIndexMask;
-		if (kind > 1 || (kind == 0 && idx >= d->n_spheres) || (kind == 1 && idx >= d->n_quads)) return fail(GS_ERR_INVALID, "bad primitive reference");
+		if (kind > 2 || (kind == 0 && idx >= d->n_spheres) || (kind == 1 && idx >= d->n_quads) || (kind == 2 && idx >= d->n_triangles))
+			return fail(GS_ERR_INVALID, "bad primitive reference");
 	}
 	return GS_OK;
 }
@@ -353,7 +372,8 @@ int gs_scene_create(const gs_scene_desc* d, int device, gs_scene** out) {
 		s->h_bfs = queue;
 	}
 	std::vector<uint32_t> refs;
-	std::vector<int> sph_new(d->n_spheres, -1), quad_new(d->n_quads, -1);
+	std::vector<int> sph_new(d->n_spheres, -1), quad_new(d->n_quads, -1), tri_new(d->n_triangles, -1);
+	std::vector<DTriangle> tris; std::vector<int2> tri_aux;
 	std::vector<DSphere> spheres; std::vector<double4> sph_path; std::vector<int2> sph_aux;
 	std::vector<DQuad> quads; std::vector<int2> quad_aux; std::vector<int> quad_order;
 	{
@@ -375,6 +395,13 @@ int gs_scene_create(const gs_scene_desc* d, int device, gs_scene** out) {
 							sph_aux.push_back(make_int2(sp.material, sp.prim_id));
 						}
 						refs.push_back(GS_PRIM_REF(0u, sph_new[idx]));
+					} else if (kind == 2) {
+						if (tri_new[idx] < 0) {
+							tri_new[idx] = (int)tris.size();
+							tris.push_back(make_dtriangle(d->triangles[idx]));
+							tri_aux.push_back(make_int2(d->triangles[idx].material, d->triangles[idx].prim_id));
+						}
+						refs.push_back(GS_PRIM_REF(2u, tri_new[idx]));
 					} else {
 						if (quad_new[idx] < 0) {
 							quad_new[idx] = (int)quads.size();
@@ -389,9 +416,9 @@ int gs_scene_create(const gs_scene_desc* d, int device, gs_scene** out) {
 				if (first >= (1u << 27) - 1u) return fail(GS_ERR_UNSUPPORTED, "too many primitive references");
 				s->h_leaf_code[n] = leaf_code(first, (uint32_t)nd.ref_count);
 				if (nd.ref_count == 1) {
-					// single-primitive leaf: put (kind << 26 | index) into the link itself, count field 0
+					// single-primitive leaf: put (kind << 25 | index) into the link itself, count field 0
 					const uint32_t r = refs.back(), kind = r >> 30, idx = r & kRefIndexMask;
-					if (idx < (1u << 26)) s->h_leaf_code[n] = leaf_code((kind << 26) | idx, 0u);
+					if (idx < (1u << 25)) s->h_leaf_code[n] = leaf_code((kind << 25) | idx, 0u);
 				}
 			} else { stack.push_back(nd.right); stack.push_back(nd.left); }
 		}
@@ -414,6 +441,7 @@ int gs_scene_create(const gs_scene_desc* d, int device, gs_scene** out) {
 	GS_CUDA(s->refs.upload(refs));
 	GS_CUDA(s->spheres.upload(spheres)); GS_CUDA(s->sph_path.upload(sph_path)); GS_CUDA(s->sph_aux.upload(sph_aux));
 	GS_CUDA(s->quads.upload(quads)); GS_CUDA(s->quad_aux.upload(quad_aux)); GS_CUDA(s->quad_order.upload(quad_order));
+	GS_CUDA(s->tris.upload(tris)); GS_CUDA(s->tri_aux.upload(tri_aux));
 	s->h2d_bytes += refs.size() * 4 + spheres.size() * (sizeof(DSphere) + sizeof(double4) + sizeof(int2)) + quads.size() * (sizeof(DQuad) + sizeof(int2) + 4);
 	{
 		std::vector<DSphere> bs; std::vector<double4> bp; std::vector<DQuad> bq;
@@ -496,6 +524,8 @@ int gs_scene_create(const gs_scene_desc* d, int device, gs_scene** out) {
 	DeviceScene& ds = s->ds;
 	ds.refs = s->refs.p; ds.spheres = s->spheres.p; ds.sph_path = s->sph_path.p; ds.sph_aux = s->sph_aux.p;
 	ds.quads = s->quads.p; ds.quad_aux = s->quad_aux.p; ds.quad_order = s->quad_order.p;
+	ds.tris = s->tris.p; ds.tri_aux = s->tri_aux.p;
+	s->has_triangles = !tris.empty();
 	ds.bnd_spheres = s->bnd_spheres.p; ds.bnd_sph_path = s->bnd_sph_path.p; ds.bnd_quads = s->bnd_quads.p;
 	ds.media = s->media.p; ds.materials = s->materials.p; ds.textures = s->textures.p; ds.images = s->images.p;
 	ds.perlin_perm = s->perm.p; ds.n_media = (int)d->n_media;
@@ -537,7 +567,7 @@ static int render_wavefront(gs_scene* s, WavefrontParams& p, cudaStream_t st) {
 	for (int wave = 0;; ++wave) {
 		GS_CUDA(launch_wf_generate(p, wave == 0, st));
 		GS_CUDA(cudaMemsetAsync(&p.ctr->next_ray, 0, 2 * sizeof(unsigned), st));  // next_ray and n_free
-		GS_CUDA(launch_wf_traverse(p, s->sm_count, s->count_nodes, st));
+		GS_CUDA(launch_wf_traverse(p, s->sm_count, s->count_nodes, s->has_triangles, st));
 		GS_CUDA(launch_wf_shade(p, st));
 		s->launches += 3;
 		if (wave % kCheckEvery == kCheckEvery - 1) {
@@ -577,7 +607,7 @@ int gs_render_accumulate(gs_scene* s, const gs_camera* camera, uint64_t seed, ui
 	p.work_counter = next_counter(s);
 	p.stats = s->stats.p;
 	GS_CUDA(cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned long long), st));
-	GS_CUDA(launch_render_fixed(p, s->sm_count, s->count_nodes, st));
+	GS_CUDA(launch_render_fixed(p, s->sm_count, s->count_nodes, s->has_triangles, st));
 	s->launches += 1;
 	return GS_OK;
 }
@@ -624,6 +654,23 @@ int gs_resolve(gs_scene* s, const void* d_accum, int32_t width, int32_t height, 
 	GS_CUDA(launch_resolve(static_cast<const float4*>(d_accum), n, s->out_rgb.p, s->out_counts.p, st));
 	s->launches += 1;
 	GS_CUDA(cudaMemcpyAsync(out_rgb, s->out_rgb.p, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+	if (out_counts) GS_CUDA(cudaMemcpyAsync(out_counts, s->out_counts.p, (size_t)n * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+	GS_CUDA(cudaStreamSynchronize(st));
+	return GS_OK;
+}
+
+int gs_resolve_rgb8(gs_scene* s, const void* d_accum, int32_t width, int32_t height, uint8_t* out_rgb8, uint32_t* out_counts, void* cuda_stream) {
+	int rc = check_device(s);
+	if (rc) return rc;
+	if (!d_accum || !out_rgb8 || width <= 0 || height <= 0) return fail(GS_ERR_INVALID, "bad resolve arguments");
+	const int n = width * height;
+	cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+	GS_CUDA(s->out_rgb.alloc((size_t)n * 3));  // reused as the byte buffer (n*3 bytes fit in n*3 floats)
+	GS_CUDA(s->out_counts.alloc((size_t)n));
+	unsigned char* d_rgb8 = reinterpret_cast<unsigned char*>(s->out_rgb.p);
+	GS_CUDA(launch_resolve_rgb8(static_cast<const float4*>(d_accum), n, d_rgb8, s->out_counts.p, st));
+	s->launches += 1;
+	GS_CUDA(cudaMemcpyAsync(out_rgb8, d_rgb8, (size_t)n * 3, cudaMemcpyDeviceToHost, st));
 	if (out_counts) GS_CUDA(cudaMemcpyAsync(out_counts, s->out_counts.p, (size_t)n * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
 	GS_CUDA(cudaStreamSynchronize(st));
 	return GS_OK;

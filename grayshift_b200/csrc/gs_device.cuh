@@ -31,7 +31,7 @@ struct __align__(16) DNode {
 	int4 link;   // child0, child1 (>= 0 internal node index; < 0 leaf code), unused, unused
 };
 // leaf code: -1 - ((first_ref << 4) | count), 1 <= count <= 15; count == 0 marks a single-primitive leaf whose
-// reference (kind << 26 | index) sits in the first_ref field itself
+// reference (kind << 25 | index) sits in the first_ref field itself
 __host__ __device__ inline int leaf_code(uint32_t first, uint32_t count) { return -1 - (int)((first << 4) | count); }
 // Negative (so the inner "internal node" loop stops on it) and not a valid leaf code: it would need
 // first_ref = 2^27 - 1 with count 15, which gs_scene_create rejects.
@@ -43,6 +43,11 @@ struct __align__(16) DQuad {
 	double nx, ny, nz, d;    // unit plane normal and offset (quad.rs:32-36, plane.rs:15-18)
 	double ax, ay, az, qa;   // alpha = P.A - qa with A = v x w    (== w . (planar x v), quad.rs:88)
 	double bx, by, bz, qb;   // beta  = P.B - qb with B = w x u    (== w . (u x planar), quad.rs:89)
+};
+struct __align__(16) DTriangle {
+	double ax, ay, az, pad0;     // vertex a
+	double e1x, e1y, e1z, pad1;  // edge_1 = c - a (triangle.rs:35)
+	double e2x, e2y, e2z, pad2;  // edge_2 = b - a (triangle.rs:36)
 };
 struct __align__(16) DMaterial { int kind; int tex; float ar, ag, ab; float param; int pad0, pad1; };
 struct __align__(16) DTexture { int kind; int a; int b; float scale; float cr, cg, cb; float pad; double scale_inv_d; double scale_d; };
@@ -61,6 +66,8 @@ struct DeviceScene {
 	const DQuad* quads;
 	const int2* quad_aux;
 	const int* quad_order;  // reference visiting rank, read only on exact-t ties
+	const DTriangle* tris;
+	const int2* tri_aux;
 	const DSphere* bnd_spheres;
 	const double4* bnd_sph_path;
 	const DQuad* bnd_quads;
@@ -180,6 +187,27 @@ __device__ __forceinline__ bool hit_quad(const DQuad& q, const Ray& r, double tm
 	return true;
 }
 
+// Triangle::hit, triangle.rs:34-68: Moeller-Trumbore as the reference writes it (back faces culled, det < 1e-8),
+// plus the interval test the reference forgets (strict like the spheres).  u, v are the reference's.
+__device__ __forceinline__ bool hit_triangle(const DTriangle& tr, const Ray& r, double tmin, double tmax, double& t_out, double& u_out,
+                                             double& v_out) {
+	const double px = r.dy * tr.e2z - r.dz * tr.e2y, py = r.dz * tr.e2x - r.dx * tr.e2z, pz = r.dx * tr.e2y - r.dy * tr.e2x;  // d x edge_2
+	const double det = tr.e1x * px + tr.e1y * py + tr.e1z * pz;
+	if (det < 1e-8) return false;
+	const double tx = r.ox - tr.ax, ty = r.oy - tr.ay, tz = r.oz - tr.az;
+	double u = tx * px + ty * py + tz * pz;
+	if (u < 0.0 || u > det) return false;
+	const double qx = ty * tr.e1z - tz * tr.e1y, qy = tz * tr.e1x - tx * tr.e1z, qz = tx * tr.e1y - ty * tr.e1x;  // t_vec x edge_1
+	double v = r.dx * qx + r.dy * qy + r.dz * qz;
+	if (v < 0.0 || u + v > det) return false;
+	double t = tr.e2x * qx + tr.e2y * qy + tr.e2z * qz;
+	const double inv_det = 1.0 / det;
+	t *= inv_det; u *= inv_det; v *= inv_det;
+	if (!(tmin < t && t < tmax)) return false;
+	t_out = t; u_out = u; v_out = v;
+	return true;
+}
+
 __device__ __forceinline__ DSphere load_sphere(const DSphere* __restrict__ p, uint32_t i) {
 	const double2* q = reinterpret_cast<const double2*>(p + i);
 	double2 a = __ldg(q), b = __ldg(q + 1);
@@ -189,6 +217,12 @@ __device__ __forceinline__ DQuad load_quad(const DQuad* __restrict__ p, uint32_t
 	const double2* q = reinterpret_cast<const double2*>(p + i);
 	double2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3), e = __ldg(q + 4), f = __ldg(q + 5);
 	return DQuad{a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y, e.x, e.y, f.x, f.y};
+}
+
+__device__ __forceinline__ DTriangle load_triangle(const DTriangle* __restrict__ p, uint32_t i) {
+	const double2* q = reinterpret_cast<const double2*>(p + i);
+	double2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3), e = __ldg(q + 4), f = __ldg(q + 5);
+	return DTriangle{a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y, e.x, e.y, f.x, f.y};
 }
 
 __device__ __forceinline__ float safe_rcp(float d) {
@@ -272,19 +306,26 @@ __device__ __forceinline__ void node_step(const DeviceScene& sc, const RayConsts
 }
 
 // One leaf: HittableList::hit over its primitives (hittable.rs:70-86) with the reference's interval rules, then pop.
-// Precondition: tv.node is a leaf code.
+// Precondition: tv.node is a leaf code.  kTris = the scene holds triangles (kernels for scenes without any are
+// instantiated without the triangle branch: it costs registers and instruction-cache space in the hot loop).
+template <bool kTris>
 __device__ __forceinline__ void leaf_step(const DeviceScene& sc, const Ray& r, RayConsts& rc, double tmin, TravState& tv, int* stack) {
 	Hit& best = tv.best;
 	const uint32_t code = (uint32_t)(-1 - tv.node);
 	uint32_t first = code >> 4, count = code & 15u;
-	// count == 0: a single-primitive leaf whose reference is stored in the link itself (kind << 26 | index):
+	// count == 0: a single-primitive leaf whose reference is stored in the link itself (kind << 25 | index):
 	// no dependent load from `refs` between the node and the primitive
 	const bool direct = count == 0u;
 	if (direct) count = 1u;
 	for (uint32_t k = 0; k < count; ++k) {
-		const uint32_t ref = direct ? (((first >> 26) << kRefKindShift) | (first & ((1u << 26) - 1u))) : __ldg(sc.refs + first + k);
+		const uint32_t ref = direct ? (((first >> 25) << kRefKindShift) | (first & ((1u << 25) - 1u))) : __ldg(sc.refs + first + k);
 		const uint32_t index = ref & kRefIndexMask;
-		if ((ref >> kRefKindShift) == 0u) {
+		const uint32_t kind = ref >> kRefKindShift;
+		if (kTris && kind == 2u) {
+			const DTriangle tr = load_triangle(sc.tris, index);
+			double t, u, v;
+			if (hit_triangle(tr, r, tmin, best.t, t, u, v)) { best.t = t; best.ref = ref; best.u = u; best.v = v; }
+		} else if (kind == 0u) {
 			const DSphere s = load_sphere(sc.spheres, index);
 			double t;
 			if (hit_sphere(s, sc.sph_path, index, r, rc.a, rc.inv_a, tmin, best.t, t)) { best.t = t; best.ref = ref; }
@@ -305,22 +346,22 @@ __device__ __forceinline__ void leaf_step(const DeviceScene& sc, const Ray& r, R
 }
 
 // One round of the classic while-while traversal: descend to the next leaf, intersect it.
-// Precondition: tv.node != kStackSentinel.
-template <bool kCount>
+// Precondition: tv.node != kStackSentinel.  kF: bit 0 = count node visits, bit 1 = scene holds triangles.
+template <int kF>
 __device__ __forceinline__ void trav_round(const DeviceScene& sc, const Ray& r, RayConsts& rc, double tmin, TravState& tv, int* stack,
                                            uint32_t* node_visits) {
-	while (tv.node >= 0) node_step<kCount>(sc, rc, tv, stack, node_visits);
-	if (tv.node != kStackSentinel) leaf_step(sc, r, rc, tmin, tv, stack);
+	while (tv.node >= 0) node_step<(kF & 1) != 0>(sc, rc, tv, stack, node_visits);
+	if (tv.node != kStackSentinel) leaf_step<(kF & 2) != 0>(sc, r, rc, tmin, tv, stack);
 }
 
 // Run-to-completion form (parity kernel, adaptive kernel, per-path hooks).
-template <bool kCount>
+template <int kF>
 __device__ __forceinline__ Hit trace_closest(const DeviceScene& sc, const Ray& r, double tmin, double tmax, uint32_t* node_visits = nullptr) {
 	int stack[kMaxStack];
 	TravState tv;
 	trav_init(sc, tv, stack, tmax);
 	RayConsts rc = ray_consts(r, tmax);
-	while (tv.node != kStackSentinel) trav_round<kCount>(sc, r, rc, tmin, tv, stack, node_visits);
+	while (tv.node != kStackSentinel) trav_round<kF>(sc, r, rc, tmin, tv, stack, node_visits);
 	return tv.best;
 }
 

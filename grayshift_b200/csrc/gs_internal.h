@@ -30,16 +30,17 @@ struct AdaptiveParams {
 };
 
 // launch wrappers (defined next to the kernels); all asynchronous on `stream`
-cudaError_t launch_render_fixed(const RenderParams& p, int sm_count, bool count_nodes, cudaStream_t stream);
+cudaError_t launch_render_fixed(const RenderParams& p, int sm_count, bool count_nodes, bool triangles, cudaStream_t stream);
 cudaError_t launch_render_adaptive(const AdaptiveParams& p, int sm_count, cudaStream_t stream);
 cudaError_t launch_resolve(const float4* accum, int n_pixels, float* out_rgb, unsigned* out_counts, cudaStream_t stream);
+cudaError_t launch_resolve_rgb8(const float4* accum, int n_pixels, unsigned char* out_rgb8, unsigned* out_counts, cudaStream_t stream);
 cudaError_t launch_camera_rays(const DCamera& cam, unsigned long long seed, unsigned sample, int pixel_begin, int pixel_end, double* rays_out,
                                cudaStream_t stream);
 cudaError_t launch_path_radiance(const DeviceScene& sc, const DCamera& cam, unsigned long long seed, const unsigned* pixel,
                                  const unsigned* sample, size_t n, float* out_rgb, cudaStream_t stream);
 cudaError_t launch_trace_closest(const DeviceScene& sc, const double* rays, size_t n, double tmin, double tmax, int* prim_id, double* t,
                                  cudaStream_t stream);
-int render_fixed_blocks_per_sm(bool count_nodes);
+int render_fixed_blocks_per_sm(bool count_nodes, bool triangles);
 
 // ---- wavefront pipeline (wavefront_kernels.cu) -------------------------------------------------------
 // Path pool: structure of arrays in HBM, one slot per in-flight path, every field a 16-byte record so each
@@ -76,7 +77,7 @@ struct WavefrontParams {
 };
 
 cudaError_t launch_wf_generate(const WavefrontParams& p, bool first_wave, cudaStream_t stream);
-cudaError_t launch_wf_traverse(const WavefrontParams& p, int sm_count, bool count_nodes, cudaStream_t stream);
+cudaError_t launch_wf_traverse(const WavefrontParams& p, int sm_count, bool count_nodes, bool triangles, cudaStream_t stream);
 cudaError_t launch_wf_shade(const WavefrontParams& p, cudaStream_t stream);
 
 }  // namespace gs

@@ -351,6 +351,7 @@ __device__ __forceinline__ bool segment_begin(const DeviceScene& sc, const DCame
 
 // The rest of the level: miss -> background; hit -> emitted + scatter.  `h` is the closest surface hit found with
 // tmax = the medium candidate.  Returns true when the path is finished; st.L then holds the sample colour.
+template <bool kTris>
 __device__ __forceinline__ bool segment_shade(const DeviceScene& sc, const DCamera& cam, const uint8_t* __restrict__ perm, PathState& st,
                                               PathCounters& pc, const Hit& h, double tmax, int medium_hit) {
 	Ray& ray = st.ray;
@@ -365,7 +366,14 @@ __device__ __forceinline__ bool segment_shade(const DeviceScene& sc, const DCame
 	if (h.ref != kNoHit) {
 		const uint32_t index = h.ref & kRefIndexMask;
 		s.px = ray.ox + ray.dx * h.t; s.py = ray.oy + ray.dy * h.t; s.pz = ray.oz + ray.dz * h.t;  // ray.at(t)
-		if ((h.ref >> kRefKindShift) == 0u) {
+		if (kTris && (h.ref >> kRefKindShift) == 2u) {
+			// Triangle: normal = (b - a) x (c - a), handed on UNNORMALISED exactly like triangle.rs:21,63 (Lambertian
+			// normalises it in its ONB; Metal and Dielectric reflect about it as it is)
+			const DTriangle tr = load_triangle(sc.tris, index);
+			n_out = mk3((float)(tr.e2y * tr.e1z - tr.e2z * tr.e1y), (float)(tr.e2z * tr.e1x - tr.e2x * tr.e1z), (float)(tr.e2x * tr.e1y - tr.e2y * tr.e1x));
+			s.is_sphere = false; s.u = (float)h.u; s.v = (float)h.v;
+			s.material = __ldg(sc.tri_aux + index).x;
+		} else if ((h.ref >> kRefKindShift) == 0u) {
 			DSphere sp = load_sphere(sc.spheres, index);
 			double cx = sp.cx, cy = sp.cy, cz = sp.cz, rad = sp.r;
 			if (rad < 0.0) { double4 p = sc.sph_path[index]; cx += ray.time * p.x; cy += ray.time * p.y; cz += ray.time * p.z; rad = -rad; }
@@ -401,14 +409,14 @@ __device__ __forceinline__ bool segment_shade(const DeviceScene& sc, const DCame
 }
 
 // One whole level, run to completion (adaptive kernel and the per-path hooks).
-template <bool kCount>
+template <int kF>
 __device__ __forceinline__ bool path_step(const DeviceScene& sc, const DCamera& cam, const uint8_t* __restrict__ perm, PathState& st,
                                           PathCounters& pc) {
 	double tmax;
 	int medium_hit;
 	if (!segment_begin(sc, cam, st, pc, tmax, medium_hit)) return true;
-	Hit h = trace_closest<kCount>(sc, st.ray, 0.001, tmax, &pc.node_visits);
-	return segment_shade(sc, cam, perm, st, pc, h, tmax, medium_hit);
+	Hit h = trace_closest<kF>(sc, st.ray, 0.001, tmax, &pc.node_visits);
+	return segment_shade<(kF & 2) != 0>(sc, cam, perm, st, pc, h, tmax, medium_hit);
 }
 
 }  // namespace gs

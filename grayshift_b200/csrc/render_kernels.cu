@@ -35,7 +35,8 @@ enum LaneState : int { kDead = 0, kTraverse = 1, kShade = 2, kSetup = 3 };
 #endif
 constexpr int kMinShade = GS_MIN_SHADE;
 
-template <bool kCount>
+// kF: bit 0 = count BVH node visits, bit 1 = the scene holds triangles
+template <int kF>
 __global__ void __launch_bounds__(kBlock, GS_MIN_BLOCKS) render_fixed_kernel(const __grid_constant__ RenderParams P) {
 	__shared__ uint8_t s_perm[256];
 	load_perm(s_perm, P.sc.perlin_perm);
@@ -67,7 +68,7 @@ __global__ void __launch_bounds__(kBlock, GS_MIN_BLOCKS) render_fixed_kernel(con
 	for (;;) {
 		// ---- phase A1: shade the lanes whose traversal finished --------------------------------------
 		if (state == kShade) {
-			if (segment_shade(P.sc, P.cam, s_perm, st, pc, tv.best, seg_tmax, seg_medium)) finish_path();
+			if (segment_shade<(kF & 2) != 0>(P.sc, P.cam, s_perm, st, pc, tv.best, seg_tmax, seg_medium)) finish_path();
 			else state = kSetup;
 		}
 		// ---- phase A2: dead lanes take the next (pixel, sample) items ------------------------------------
@@ -122,18 +123,18 @@ __global__ void __launch_bounds__(kBlock, GS_MIN_BLOCKS) render_fixed_kernel(con
 			if ((m_node | m_leaf) == 0u || __popc(m_shade) >= kMinShade) break;
 			if (__popc(m_node) >= __popc(m_leaf)) {
 				if (at_node) {
-					node_step<kCount>(P.sc, rc, tv, stack, &pc.node_visits);
-					if (tv.node >= 0) node_step<kCount>(P.sc, rc, tv, stack, &pc.node_visits);
+					node_step<(kF & 1) != 0>(P.sc, rc, tv, stack, &pc.node_visits);
+					if (tv.node >= 0) node_step<(kF & 1) != 0>(P.sc, rc, tv, stack, &pc.node_visits);
 				}
 			} else if (trav && !at_node) {
-				leaf_step(P.sc, st.ray, rc, 0.001, tv, stack);
+				leaf_step<(kF & 2) != 0>(P.sc, st.ray, rc, 0.001, tv, stack);
 			}
 			if (trav && tv.node == kStackSentinel) state = kShade;
 		}
 #elif GS_MIN_SHADE >= 32
 		// Every lane runs its ray to completion (classic while-while); measured best on B200.
 		if (state == kTraverse) {
-			while (tv.node != kStackSentinel) trav_round<kCount>(P.sc, st.ray, rc, 0.001, tv, stack, &pc.node_visits);
+			while (tv.node != kStackSentinel) trav_round<kF>(P.sc, st.ray, rc, 0.001, tv, stack, &pc.node_visits);
 			state = kShade;
 		}
 #else
@@ -144,7 +145,7 @@ __global__ void __launch_bounds__(kBlock, GS_MIN_BLOCKS) render_fixed_kernel(con
 			const unsigned m_shade = __ballot_sync(kFull, state == kShade);
 			if (m_trav == 0u || __popc(m_shade) >= kMinShade) break;
 			if (trav) {
-				trav_round<kCount>(P.sc, st.ray, rc, 0.001, tv, stack, &pc.node_visits);
+				trav_round<kF>(P.sc, st.ray, rc, 0.001, tv, stack, &pc.node_visits);
 				if (tv.node == kStackSentinel) state = kShade;
 			}
 		}
@@ -193,7 +194,7 @@ __global__ void __launch_bounds__(kBlock) render_adaptive_kernel(const __grid_co
 					next += need < avail ? need : avail;
 				}
 				if (!__any_sync(kFull, alive)) break;
-				if (alive && path_step<false>(P.sc, P.cam, s_perm, st, pc)) {
+				if (alive && path_step<2>(P.sc, P.cam, s_perm, st, pc)) {
 					cr += (double)st.L.x; cg += (double)st.L.y; cb += (double)st.L.z;
 					const double lum = 0.299 * (double)st.L.x + 0.587 * (double)st.L.y + 0.144 * (double)st.L.z;  // color.rs:31-33
 					sum += lum; sq_sum += lum * lum;
@@ -224,6 +225,24 @@ __global__ void resolve_kernel(const float4* __restrict__ accum, int n_pixels, f
 	if (out_counts) out_counts[i] = (unsigned)a.w;
 }
 
+// the same fused with write_color's transfer (color.rs:8-26): the bytes of the reference's image.ppm
+__global__ void resolve_rgb8_kernel(const float4* __restrict__ accum, int n_pixels, uchar3* __restrict__ out_rgb8, unsigned* __restrict__ out_counts) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_pixels) return;
+	float4 a = accum[i];
+	float inv = a.w > 0.f ? 1.0f / a.w : 0.f;
+	const float c[3] = {a.x * inv, a.y * inv, a.z * inv};
+	unsigned char q[3];
+#pragma unroll
+	for (int k = 0; k < 3; ++k) {
+		double g = c[k] > 0.0f ? sqrt((double)c[k]) : 0.0;  // linear_to_gamma
+		g = g < 0.0 ? 0.0 : (g > 0.999 ? 0.999 : g);          // INTENSITY.clamp
+		q[k] = (unsigned char)(int)(256.0 * g);
+	}
+	out_rgb8[i] = make_uchar3(q[0], q[1], q[2]);
+	if (out_counts) out_counts[i] = (unsigned)a.w;
+}
+
 __global__ void camera_rays_kernel(const __grid_constant__ DCamera cam, unsigned long long seed, unsigned sample, int pixel_begin, int pixel_end,
                                    double* __restrict__ rays_out) {
 	int n = pixel_begin + blockIdx.x * blockDim.x + threadIdx.x;
@@ -245,26 +264,37 @@ __global__ void __launch_bounds__(kBlock) path_radiance_kernel(const __grid_cons
 	PathCounters pc = {0u, 0u, 0u};
 	PathState st;
 	path_begin(st, cam, seed, pixel[k], sample[k]);
-	while (!path_step<false>(sc, cam, s_perm, st, pc)) {}
+	while (!path_step<2>(sc, cam, s_perm, st, pc)) {}
 	out_rgb[k * 3 + 0] = st.L.x; out_rgb[k * 3 + 1] = st.L.y; out_rgb[k * 3 + 2] = st.L.z;
 }
 
 // ---- launch wrappers ------------------------------------------------------------------------------
-int render_fixed_blocks_per_sm(bool count_nodes) {
+template <int kF>
+static void fixed_occupancy(int* n) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(n, render_fixed_kernel<kF>, kBlock, 0); }
+
+int render_fixed_blocks_per_sm(bool count_nodes, bool triangles) {
 	int n = 0;
-	if (count_nodes) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, render_fixed_kernel<true>, kBlock, 0);
-	else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, render_fixed_kernel<false>, kBlock, 0);
+	switch ((count_nodes ? 1 : 0) | (triangles ? 2 : 0)) {
+		case 0: fixed_occupancy<0>(&n); break;
+		case 1: fixed_occupancy<1>(&n); break;
+		case 2: fixed_occupancy<2>(&n); break;
+		default: fixed_occupancy<3>(&n); break;
+	}
 	return n > 0 ? n : 1;
 }
 
-cudaError_t launch_render_fixed(const RenderParams& p, int sm_count, bool count_nodes, cudaStream_t stream) {
-	const int per_sm = render_fixed_blocks_per_sm(count_nodes);
+cudaError_t launch_render_fixed(const RenderParams& p, int sm_count, bool count_nodes, bool triangles, cudaStream_t stream) {
+	const int per_sm = render_fixed_blocks_per_sm(count_nodes, triangles);
 	unsigned long long warps_needed = (p.total_items + 31ull) / 32ull;
 	unsigned long long blocks_needed = (warps_needed + (kBlock / 32) - 1) / (kBlock / 32);
 	unsigned long long grid = (unsigned long long)sm_count * per_sm;  // persistent: SMs x resident CTAs
 	if (blocks_needed < grid) grid = blocks_needed ? blocks_needed : 1;
-	if (count_nodes) render_fixed_kernel<true><<<(unsigned)grid, kBlock, 0, stream>>>(p);
-	else render_fixed_kernel<false><<<(unsigned)grid, kBlock, 0, stream>>>(p);
+	switch ((count_nodes ? 1 : 0) | (triangles ? 2 : 0)) {
+		case 0: render_fixed_kernel<0><<<(unsigned)grid, kBlock, 0, stream>>>(p); break;
+		case 1: render_fixed_kernel<1><<<(unsigned)grid, kBlock, 0, stream>>>(p); break;
+		case 2: render_fixed_kernel<2><<<(unsigned)grid, kBlock, 0, stream>>>(p); break;
+		default: render_fixed_kernel<3><<<(unsigned)grid, kBlock, 0, stream>>>(p); break;
+	}
 	return cudaGetLastError();
 }
 
@@ -281,6 +311,11 @@ cudaError_t launch_render_adaptive(const AdaptiveParams& p, int sm_count, cudaSt
 
 cudaError_t launch_resolve(const float4* accum, int n_pixels, float* out_rgb, unsigned* out_counts, cudaStream_t stream) {
 	resolve_kernel<<<(n_pixels + 255) / 256, 256, 0, stream>>>(accum, n_pixels, out_rgb, out_counts);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_resolve_rgb8(const float4* accum, int n_pixels, unsigned char* out_rgb8, unsigned* out_counts, cudaStream_t stream) {
+	resolve_rgb8_kernel<<<(n_pixels + 255) / 256, 256, 0, stream>>>(accum, n_pixels, reinterpret_cast<uchar3*>(out_rgb8), out_counts);
 	return cudaGetLastError();
 }
 

@@ -13,10 +13,11 @@ __global__ void __launch_bounds__(128) trace_closest_kernel(const __grid_constan
 	const double* rp = rays + k * 7;
 	Ray r;
 	r.ox = rp[0]; r.oy = rp[1]; r.oz = rp[2]; r.dx = rp[3]; r.dy = rp[4]; r.dz = rp[5]; r.time = rp[6];
-	Hit h = trace_closest<false>(sc, r, tmin, tmax);
+	Hit h = trace_closest<2>(sc, r, tmin, tmax);
 	if (h.ref == kNoHit) { prim_id[k] = -1; t_out[k] = 0.0; return; }
 	const uint32_t index = h.ref & kRefIndexMask;
-	prim_id[k] = (h.ref >> kRefKindShift) == 0u ? sc.sph_aux[index].y : sc.quad_aux[index].y;
+	const uint32_t kind = h.ref >> kRefKindShift;
+	prim_id[k] = kind == 0u ? sc.sph_aux[index].y : (kind == 1u ? sc.quad_aux[index].y : sc.tri_aux[index].y);
 	t_out[k] = h.t;
 }
 

@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(kBlock) wf_generate_kernel(const __grid_consta
 }
 
 // ---- traverse ------------------------------------------------------------------------------------------
-template <bool kCount>
+template <int kF>
 __global__ void __launch_bounds__(kBlock) wf_traverse_kernel(const __grid_constant__ WavefrontParams P) {
 	const unsigned lane = threadIdx.x & 31u;
 	const unsigned lt = lanemask_lt();
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(kBlock) wf_traverse_kernel(const __grid_consta
 			continue;
 		}
 		if (slot >= 0) {
-			trav_round<kCount>(P.sc, ray, rc, 0.001, tv, stack, &pc.node_visits);
+			trav_round<kF>(P.sc, ray, rc, 0.001, tv, stack, &pc.node_visits);
 			if (tv.node == kStackSentinel) {
 				// closest event: surface hit (ref), else medium event (t = the medium's candidate), else miss
 				reinterpret_cast<double*>(P.pool.dir + slot)[3] = tv.best.t;
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(kBlock) wf_shade_kernel(const __grid_constant_
 		if (id.z & 3u) st.rng.buf = philox4x32_10(id.x, id.y, id.z >> 2, 0u, st.rng.k0, st.rng.k1);
 		Hit h;
 		h.t = d.w; h.ref = hw.x; h.u = (double)__uint_as_float(hw.z); h.v = (double)__uint_as_float(hw.w);
-		bool finished = segment_shade(P.sc, P.cam, s_perm, st, pc, h, d.w, (int)hw.y);
+		bool finished = segment_shade<true>(P.sc, P.cam, s_perm, st, pc, h, d.w, (int)hw.y);
 		if (!finished && st.bounce >= P.cam.max_depth) finished = true;  // the next level returns ZERO (camera.rs:175)
 		if (finished) {
 			red_add_v4(P.accum + st.pixel, st.L.x, st.L.y, st.L.z, 1.0f);  // pixel_color += sample_color (camera.rs:141)
@@ -194,17 +194,25 @@ cudaError_t launch_wf_generate(const WavefrontParams& p, bool first_wave, cudaSt
 	return cudaGetLastError();
 }
 
-cudaError_t launch_wf_traverse(const WavefrontParams& p, int sm_count, bool count_nodes, cudaStream_t stream) {
+template <int kF>
+static cudaError_t wf_traverse_launch(const WavefrontParams& p, int sm_count, cudaStream_t stream) {
 	int per_sm = 0;
-	if (count_nodes) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_traverse_kernel<true>, kBlock, 0);
-	else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_traverse_kernel<false>, kBlock, 0);
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_traverse_kernel<kF>, kBlock, 0);
 	if (per_sm < 1) per_sm = 1;
 	long long grid = (long long)sm_count * per_sm;  // persistent: SMs x resident CTAs
 	const long long needed = (p.pool.n + kBlock - 1) / kBlock;
 	if (needed < grid) grid = needed;
-	if (count_nodes) wf_traverse_kernel<true><<<(unsigned)grid, kBlock, 0, stream>>>(p);
-	else wf_traverse_kernel<false><<<(unsigned)grid, kBlock, 0, stream>>>(p);
+	wf_traverse_kernel<kF><<<(unsigned)grid, kBlock, 0, stream>>>(p);
 	return cudaGetLastError();
+}
+
+cudaError_t launch_wf_traverse(const WavefrontParams& p, int sm_count, bool count_nodes, bool triangles, cudaStream_t stream) {
+	switch ((count_nodes ? 1 : 0) | (triangles ? 2 : 0)) {
+		case 0: return wf_traverse_launch<0>(p, sm_count, stream);
+		case 1: return wf_traverse_launch<1>(p, sm_count, stream);
+		case 2: return wf_traverse_launch<2>(p, sm_count, stream);
+		default: return wf_traverse_launch<3>(p, sm_count, stream);
+	}
 }
 
 cudaError_t launch_wf_shade(const WavefrontParams& p, cudaStream_t stream) {

@@ -27,6 +27,11 @@ class gs_quad(C.Structure):
                 ("reserved", C.c_int32)]
 
 
+class gs_triangle(C.Structure):
+    _fields_ = [("a", d3), ("b", d3), ("c", d3), ("material", C.c_int32), ("prim_id", C.c_int32), ("order", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
 class gs_bvh_node(C.Structure):
     _fields_ = [("bounds_min", d3), ("bounds_max", d3), ("left", C.c_int32), ("right", C.c_int32), ("first_ref", C.c_int32),
                 ("ref_count", C.c_int32)]
@@ -61,7 +66,8 @@ class gs_scene_desc(C.Structure):
                 ("materials", C.POINTER(gs_material)), ("n_materials", C.c_size_t),
                 ("textures", C.POINTER(gs_texture)), ("n_textures", C.c_size_t),
                 ("images", C.POINTER(gs_image)), ("n_images", C.c_size_t),
-                ("perlin_perm", C.POINTER(C.c_uint8))]
+                ("perlin_perm", C.POINTER(C.c_uint8)),
+                ("triangles", C.POINTER(gs_triangle)), ("n_triangles", C.c_size_t)]
 
 
 class gs_camera(C.Structure):
@@ -95,6 +101,7 @@ CUDA_SYMBOLS = {
                                                 C.c_uint32, C.c_void_p, C.c_void_p]),
     "gs_scene_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
     "gs_resolve": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gs_resolve_rgb8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gs_stats_read": (C.c_int, [C.c_void_p, C.POINTER(gs_stats)]),
     "gs_tonemap": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p]),
     "gs_trace_closest": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_double, C.c_double, C.c_void_p, C.c_void_p]),

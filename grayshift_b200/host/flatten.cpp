@@ -128,6 +128,24 @@ struct Flattener {
 				out.quads.push_back(g);
 				break;
 			}
+			case NodeKind::Triangle: {
+				const auto& t = static_cast<const Triangle&>(*h);
+				gs_triangle g{};
+				Vec3 a = x.point(t.a), b = x.point(t.b), c = x.point(t.c);
+				g.a[0] = a.x; g.a[1] = a.y; g.a[2] = a.z; g.b[0] = b.x; g.b[1] = b.y; g.b[2] = b.z; g.c[0] = c.x; g.c[1] = c.y; g.c[2] = c.z;
+				g.material = material(t.material);
+				g.prim_id = t.prim_id;
+				g.order = next_order++;
+				double bd[6];
+				for (int k = 0; k < 3; ++k) {
+					bd[k] = std::fmin(g.a[k], std::fmin(g.b[k], g.c[k]));
+					bd[k + 3] = std::fmax(g.a[k], std::fmax(g.b[k], g.c[k]));
+				}
+				bounds.insert(bounds.end(), bd, bd + 6);
+				refs.push_back(GS_PRIM_REF(GS_PRIM_TRIANGLE, out.triangles.size()));
+				out.triangles.push_back(g);
+				break;
+			}
 			case NodeKind::List:
 				for (const auto& o : static_cast<const HittableList&>(*h).objects) walk(o, x);
 				break;
@@ -208,6 +226,8 @@ struct Flattener {
 				walk_boundary(r.object, y);
 				break;
 			}
+			case NodeKind::Triangle:
+				throw std::runtime_error("flatten: a triangle cannot bound a ConstantMedium (boundaries are spheres or quads)");
 			case NodeKind::Medium:
 				throw std::runtime_error("flatten: a ConstantMedium cannot bound another medium");
 		}
@@ -380,6 +400,7 @@ void FlatScene::finish() {
 		images[i].pixels = image_data[i]->format == GS_IMG_U8_RGB ? (const void*)image_data[i]->u8.data() : (const void*)image_data[i]->f32.data();
 	desc.images = images.data(); desc.n_images = images.size();
 	desc.perlin_perm = has_noise ? perlin_perm : nullptr;
+	desc.triangles = triangles.data(); desc.n_triangles = triangles.size();
 }
 
 std::unique_ptr<FlatScene> flatten(const HittablePtr& world, const FlattenOptions& opt) {

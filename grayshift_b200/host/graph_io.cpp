@@ -5,7 +5,7 @@
 //   texture <id> solid r g b | checker scale <even> <odd> | image <image> | noise scale
 //   material <id> lambertian <tex> | metal r g b fuzz | dielectric ir | light <tex> | isotropic <tex>
 //   node <id> sphere c(3) r <mat> <prim> | msphere c1(3) c2(3) r <mat> <prim> | quad q(3) u(3) v(3) <mat> <prim>
-//           | list n ids.. | bvh n ids.. | translate <child> off(3) | rotate_y <child> deg
+//           | tri a(3) b(3) c(3) <mat> <prim> | list n ids.. | bvh n ids.. | translate <child> off(3) | rotate_y <child> deg
 //           | medium <boundary> density <phase mat> <medium index>
 //   root <id>
 //   camera aspect width confidence tolerance batch max depth vfov from(3) at(3) vup(3) defocus focus
@@ -97,6 +97,12 @@ struct Writer {
 				const auto& q = static_cast<const Quad&>(*h);
 				int m = material(q.material);
 				rec = "quad " + vec(q.q) + " " + vec(q.u) + " " + vec(q.v) + " " + std::to_string(m) + " " + std::to_string(q.prim_id);
+				break;
+			}
+			case NodeKind::Triangle: {
+				const auto& t = static_cast<const Triangle&>(*h);
+				int m = material(t.material);
+				rec = "tri " + vec(t.a) + " " + vec(t.b) + " " + vec(t.c) + " " + std::to_string(m) + " " + std::to_string(t.prim_id);
 				break;
 			}
 			case NodeKind::List: children("list", static_cast<const HittableList&>(*h).objects); break;
@@ -212,7 +218,7 @@ HostScene load_graph(const std::string& path, bool include_media) {
 			if (ty == "sphere") { Vec3 c = V(is); double r; int m, pid; is >> r >> m >> pid; auto s = Sphere::new_stationary(c, r, materials.at(m)); s->prim_id = pid; nodes[id] = s; }
 			else if (ty == "msphere") { Vec3 c1 = V(is), c2 = V(is); double r; int m, pid; is >> r >> m >> pid; auto s = Sphere::new_moving(c1, c2, r, materials.at(m)); s->prim_id = pid; nodes[id] = s; }
 			else if (ty == "quad") { Vec3 q = V(is), u = V(is), v = V(is); int m, pid; is >> m >> pid; auto s = Quad::new_(q, u, v, materials.at(m)); s->prim_id = pid; nodes[id] = s; }
-			else if (ty == "tri") throw std::runtime_error(path + ": triangles are not built yet (SURVEY 8(f) rank 3)");
+			else if (ty == "tri") { Vec3 a = V(is), b = V(is), c = V(is); int m, pid; is >> m >> pid; auto s = Triangle::new_(a, b, c, materials.at(m)); s->prim_id = pid; nodes[id] = s; }
 			else if (ty == "list") { auto l = HittableList::new_(); for (auto& o : kids()) l->add(o); nodes[id] = l; }
 			else if (ty == "bvh") { HittableList tmp; for (auto& o : kids()) tmp.add(o); nodes[id] = BVHNode::from_list(tmp); }
 			else if (ty == "translate") { int c; is >> c; Vec3 off = V(is); auto o = nodes.at(c); nodes[id] = o ? HittablePtr(Translate::new_(o, off)) : nullptr; }

@@ -136,7 +136,7 @@ struct Isotropic : Material {
 };
 
 // ---- hittable/*.rs ----------------------------------------------------------------------------------------
-enum class NodeKind { Sphere, Quad, List, Bvh, Translate, RotateY, Medium };
+enum class NodeKind { Sphere, Quad, Triangle, List, Bvh, Translate, RotateY, Medium };
 struct Hittable {
 	NodeKind node_kind;
 	explicit Hittable(NodeKind k) : node_kind(k) {}
@@ -176,6 +176,16 @@ struct Quad : Hittable {  // quad.rs:12-80
 	Quad() : Hittable(NodeKind::Quad) {}
 	static std::shared_ptr<Quad> new_(const Vec3& q, const Vec3& u, const Vec3& v, std::shared_ptr<Material> m);
 	static std::shared_ptr<HittableList> cube(const Vec3& point_a, const Vec3& point_b, std::shared_ptr<Material> m);
+	AABB bounding_box() const override { return bbox; }
+};
+
+struct Triangle : Hittable {  // triangle.rs:10-28
+	Vec3 a, b, c;
+	std::shared_ptr<Material> material;
+	AABB bbox;
+	int prim_id = -1;
+	Triangle() : Hittable(NodeKind::Triangle) {}
+	static std::shared_ptr<Triangle> new_(const Vec3& a, const Vec3& b, const Vec3& c, std::shared_ptr<Material> m);
 	AABB bounding_box() const override { return bbox; }
 };
 
@@ -243,6 +253,7 @@ struct Background {  // camera.rs:246-249
 struct FlatScene {
 	std::vector<gs_sphere> spheres, boundary_spheres;
 	std::vector<gs_quad> quads, boundary_quads;
+	std::vector<gs_triangle> triangles;
 	std::vector<gs_bvh_node> nodes;
 	std::vector<uint32_t> prim_refs;
 	std::vector<gs_medium> media;

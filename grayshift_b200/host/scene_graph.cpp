@@ -178,6 +178,14 @@ std::shared_ptr<HittableList> Quad::cube(const Vec3& a, const Vec3& b, std::shar
 	return sides;
 }
 
+std::shared_ptr<Triangle> Triangle::new_(const Vec3& a, const Vec3& b, const Vec3& c, std::shared_ptr<Material> m) {  // triangle.rs:20-28
+	auto t = std::make_shared<Triangle>();
+	t->bbox = AABB::from_AABB_pair(AABB::from_corners(a, b), AABB::from_corners(a, c));
+	t->a = a; t->b = b; t->c = c; t->material = std::move(m);
+	t->prim_id = g_next_prim_id++;
+	return t;
+}
+
 std::shared_ptr<BVHNode> BVHNode::construct_tree(std::vector<HittablePtr> objects) {  // BVH.rs:18-65
 	if (objects.empty()) throw std::runtime_error("BVHNode::from_list: empty list (the reference recurses forever)");
 	auto node = std::make_shared<BVHNode>();

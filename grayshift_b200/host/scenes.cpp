@@ -237,6 +237,25 @@ HostScene hdri(const SceneOptions& opt) {
 	return s;
 }
 
+// main.rs:836-888
+HostScene triangles(const SceneOptions& opt) {
+	auto world = HittableList::new_();
+	auto left_red = Lambertian::from_color(Vec3::new_(1.0, 0.2, 0.2));
+	auto back_green = Lambertian::from_color(Vec3::new_(0.2, 1.0, 0.2));
+	auto right_blue = Lambertian::from_color(Vec3::new_(0.2, 0.2, 1.0));   // created, unused (main.rs:842)
+	auto upper_orange = Lambertian::from_color(Vec3::new_(1.0, 0.5, 0.0));
+	auto lower_teal = Lambertian::from_color(Vec3::new_(0.2, 0.8, 0.8));   // created, unused (main.rs:844)
+	(void)right_blue; (void)lower_teal;
+	world->add(Triangle::new_(Vec3::new_(-2.0, 2.0, 0.0), Vec3::new_(-2.0, -2.0, 0.0), Vec3::new_(-2.0, -2.0, 4.0), left_red));
+	world->add(Triangle::new_(Vec3::new_(-2.0, 2.0, 0.0), Vec3::new_(2.0, -2.0, 0.0), Vec3::new_(-2.0, -2.0, 0.0), back_green));
+	world->add(Triangle::new_(Vec3::new_(-2.0, -2.0, 4.0), Vec3::new_(-2.0, -2.0, 0.0), Vec3::new_(2.0, -2.0, 0.0), upper_orange));
+	HostScene s;
+	s.camera = make_camera({1.0, 400, S_32_1000_25, 50, 80.0, Vec3::new_(0.0, 0.0, 9.0), Vec3::ZERO, 0.0,
+	                        Background::SOLID(Vec3::new_(0.7, 0.8, 1.0))}, opt);
+	s.world = BVHNode::from_list(world);
+	return s;
+}
+
 // Config c5 (no reference counterpart): n spheres r = 0.25 in [0,100)^3, materials as main.rs:85-103.
 HostScene sphere_cloud(const SceneOptions& opt) {
 	auto world = HittableList::new_();
@@ -289,7 +308,7 @@ HostScene build_scene(const std::string& name, const SceneOptions& opt_in) {
 	else if (name == "scene8") s = final_scene(opt, 400, 50);
 	else if (name == "scene9") s = final_scene(opt, 800, 40);
 	else if (name == "scene11") s = hdri(opt);
-	else if (name == "scene10") throw std::runtime_error("scene10 (triangles) is not built yet: Triangle is a 'next' row (SURVEY 8(f) rank 3)");
+	else if (name == "scene10") s = triangles(opt);
 	else throw std::runtime_error("unknown scene '" + name + "'");
 	s.name = name;
 	return s;

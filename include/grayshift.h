@@ -68,6 +68,21 @@ typedef struct gs_quad {
 	int32_t reserved;
 } gs_quad;
 
+/* Triangle::new, src/hittable/triangle.rs:20-28.  Moeller-Trumbore with the reference's conventions: edge_1 = c - a,
+ * edge_2 = b - a, back faces culled (det < 1e-8), u = barycentric of c, v of b, normal = (b - a) x (c - a) NOT
+ * normalised (triangle.rs:21, 55-63).  ONE DELIBERATE DIFFERENCE: the reference's Triangle::hit never
+ * looks at ray_t, so a triangle visited later replaces a closer hit and even hits behind the origin count -- the
+ * result then depends on the shape of the reference's BVH.  This library applies the interval (t_min < t < closest)
+ * like every other primitive, which is order-independent; the two agree whenever no ray meets a triangle outside
+ * its interval (true for main.rs's `triangles` scene, tests/test_oracle_kat.py). */
+typedef struct gs_triangle {
+	double a[3], b[3], c[3];
+	int32_t material;
+	int32_t prim_id;
+	int32_t order;
+	int32_t reserved;
+} gs_triangle;
+
 /* ---- acceleration structure (replaces BVHNode, src/hittable/BVH.rs) ------------------------
  * A binary BVH over the surface primitives, built by the host.  The closest hit does not depend
  * on the tree's shape (every box is conservative), so the host may build any valid tree; the
@@ -82,6 +97,7 @@ typedef struct gs_bvh_node {
 
 #define GS_PRIM_SPHERE 0u
 #define GS_PRIM_QUAD 1u
+#define GS_PRIM_TRIANGLE 2u
 #define GS_PRIM_REF(kind, index) (((uint32_t)(kind) << 30) | (uint32_t)(index))
 
 /* ---- participating media (replace ConstantMedium, src/hittable/volume.rs:10-67) -------------
@@ -155,6 +171,7 @@ typedef struct gs_scene_desc {
 	const gs_texture* textures;         size_t n_textures;
 	const gs_image* images;             size_t n_images;
 	const uint8_t* perlin_perm;         /* 256-entry permutation table of noise::Perlin::default() (texture.rs:104); may be NULL without noise textures */
+	const gs_triangle* triangles;       size_t n_triangles;
 } gs_scene_desc;
 
 /* ---- camera (the private fields Camera::new computes, src/camera.rs:17-36, 80-97) ------------- */
@@ -238,6 +255,11 @@ int gs_scene_set_option(gs_scene* scene, const char* key, int64_t value);
 /* d_accum (device, W*H float4) -> host mean radiance and counts; blocking on `cuda_stream`. */
 int gs_resolve(gs_scene* scene, const void* d_accum, int32_t width, int32_t height, float* out_rgb,
                uint32_t* out_counts, void* cuda_stream);
+/* The output stage on the device: pixel_color /= sample_count (camera.rs:167) fused with write_color's
+ * transfer (color.rs:8-26: sqrt gamma, clamp to [0, 0.999], *256 truncated) -> W*H*3 bytes on the host,
+ * i.e. the numbers the reference prints into image.ppm.  A quarter of gs_resolve's device-to-host traffic. */
+int gs_resolve_rgb8(gs_scene* scene, const void* d_accum, int32_t width, int32_t height, uint8_t* out_rgb8,
+                    uint32_t* out_counts, void* cuda_stream);
 /* Device-side totals accumulated since the last call (synchronises the device). */
 int gs_stats_read(gs_scene* scene, gs_stats* stats);
 

@@ -192,6 +192,8 @@ int orc_load_hdr(const char* path, int* w, int* h, float* out) {
 		if (out) std::memcpy(out, im->rgb.data(), im->rgb.size() * sizeof(float));
 	});
 }
+void orc_set_triangle_interval(int respect) { g_triangle_respects_interval = respect != 0; }
+
 int orc_counters_enabled() {
 #ifdef ORC_COUNTERS
 	return 1;

@@ -12,6 +12,7 @@ namespace orc {
 
 thread_local Counters tls_counters;
 thread_local Rng tls_rng;
+bool g_triangle_respects_interval = false;
 
 // =========================================================================================
 // Third-party: noise 0.9.0 Perlin (call sites texture.rs:3,99,104,113-117).  UNPINNED.
@@ -330,7 +331,7 @@ Triangle::Triangle(const Vec3& a_, const Vec3& b_, const Vec3& c_, std::shared_p
 	normal = (b - a).cross(c - a);
 	bbox = AABB::from_pair(AABB::from_corners(a, b), AABB::from_corners(a, c));
 }
-std::optional<HitRecord> Triangle::hit(const Ray& ray, const Interval&) const {  // triangle.rs:34-68: ignores ray_t (Q14)
+std::optional<HitRecord> Triangle::hit(const Ray& ray, const Interval& ray_t) const {  // triangle.rs:34-68: ignores ray_t (Q14)
 	ORC_COUNT(prim_tests);
 	Vec3 edge_1 = c - a, edge_2 = b - a;
 	Vec3 p_vec = ray.direction.cross(edge_2);
@@ -345,6 +346,7 @@ std::optional<HitRecord> Triangle::hit(const Ray& ray, const Interval&) const { 
 	double t = edge_2.dot(q_vec);
 	double inv_det = 1.0 / det;
 	t *= inv_det; u *= inv_det; v *= inv_det;
+	if (g_triangle_respects_interval && !ray_t.surrounds(t)) return std::nullopt;  // NOT in the reference; see oracle.hpp
 	return HitRecord(ray, t, ray.at(t), normal, material, u, v, prim_id);
 }
 

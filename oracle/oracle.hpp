@@ -49,6 +49,9 @@ struct Counters {
 	}
 };
 extern thread_local Counters tls_counters;
+// false (default) = the reference's Triangle::hit, which ignores ray_t (Q14).  true = apply t_min < t < t_max, the
+// order-independent rule the device uses; tests compare the two on the reference's triangle scene.
+extern bool g_triangle_respects_interval;
 #ifdef ORC_COUNTERS
 #define ORC_COUNT(field) (++::orc::tls_counters.field)
 #else

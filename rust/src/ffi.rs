@@ -33,6 +33,18 @@ pub struct gs_quad {
 
 #[repr(C)]
 #[derive(Clone, Copy, Default)]
+pub struct gs_triangle {
+    pub a: [f64; 3],
+    pub b: [f64; 3],
+    pub c: [f64; 3],
+    pub material: i32,
+    pub prim_id: i32,
+    pub order: i32,
+    pub reserved: i32,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
 pub struct gs_bvh_node {
     pub bounds_min: [f64; 3],
     pub bounds_max: [f64; 3],
@@ -123,6 +135,8 @@ pub struct gs_scene_desc {
     pub images: *const gs_image,
     pub n_images: usize,
     pub perlin_perm: *const u8,
+    pub triangles: *const gs_triangle,
+    pub n_triangles: usize,
 }
 
 pub const GS_BG_SOLID: i32 = 0;
@@ -193,6 +207,8 @@ extern "C" {
                                          cuda_stream: *mut c_void) -> c_int;
     pub fn gs_resolve(scene: *mut gs_scene, d_accum: *const c_void, width: i32, height: i32, out_rgb: *mut f32,
                       out_counts: *mut u32, cuda_stream: *mut c_void) -> c_int;
+    pub fn gs_resolve_rgb8(scene: *mut gs_scene, d_accum: *const c_void, width: i32, height: i32, out_rgb8: *mut u8,
+                           out_counts: *mut u32, cuda_stream: *mut c_void) -> c_int;
     pub fn gs_stats_read(scene: *mut gs_scene, stats: *mut gs_stats) -> c_int;
     pub fn gs_tonemap(rgb: *const f32, n_pixels: usize, out_rgb8: *mut u8) -> c_int;
     pub fn gs_trace_closest(scene: *mut gs_scene, rays: *const f64, n: usize, tmin: f64, tmax: f64, prim_id: *mut i32,

@@ -252,6 +252,8 @@ impl FlatScene {
             images: self.image_descs.as_ptr(),
             n_images: self.image_descs.len(),
             perlin_perm: if self.has_noise { self.perlin_perm.as_ptr() } else { std::ptr::null() },
+            triangles: std::ptr::null(), // Triangle::flatten -> push_triangle: same pattern as push_quad (kind 2)
+            n_triangles: 0,
         }
     }
 }

@@ -89,6 +89,9 @@ class Graph:
     def quad(self, q, u, v, mat):
         return self._node(f"quad {_v(q)} {_v(u)} {_v(v)} {mat} {self._prim()}")
 
+    def triangle(self, a, b, c, mat):
+        return self._node(f"tri {_v(a)} {_v(b)} {_v(c)} {mat} {self._prim()}")
+
     def cube(self, a, b, mat):
         """Quad::cube, src/hittable/quad.rs:54-80"""
         a, b = np.asarray(a, float), np.asarray(b, float)

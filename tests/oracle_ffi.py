@@ -166,6 +166,11 @@ class OracleScene:
             pass
 
 
+def set_triangle_interval(respect, counters=False):
+    """False = the reference's Triangle::hit (ignores ray_t, Q14); True = the order-independent rule the device uses."""
+    lib(counters).orc_set_triangle_interval(int(bool(respect)))
+
+
 def philox(ctr, key):
     c = (C.c_uint32 * 4)(*ctr)
     k = (C.c_uint32 * 2)(*key)

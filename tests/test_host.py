@@ -12,7 +12,7 @@ import oracle_ffi as orc
 from grayshift_b200 import ffi
 from graphs import random_scene
 
-SCENES = ["c1", "c2", "c3", "c4", "scene0", "scene1", "scene2", "scene3", "scene4", "scene5", "scene6", "scene7", "scene8", "scene9", "scene11"]
+SCENES = ["c1", "c2", "c3", "c4", "scene0", "scene1", "scene2", "scene3", "scene4", "scene5", "scene6", "scene7", "scene8", "scene9", "scene10", "scene11"]
 
 
 @pytest.mark.parametrize("name", SCENES)

@@ -482,3 +482,63 @@ def test_random_scene_graph_roundtrip(tmp_path):
     rays = s.camera_rays(1, 0)
     a, b = s.trace_closest(rays), s2.trace_closest(rays)
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+# ---- triangle.rs:10-73 (quirk Q14) ------------------------------------------------------------------------
+def test_triangle_known_answers_and_the_ignored_interval(tmp_path):
+    def build(g):
+        m = g.lambertian_color([1, 1, 1])
+        # counter-clockwise seen from +z ... with the reference's edge naming (edge_1 = c - a, edge_2 = b - a) the
+        # FRONT face (det > 0) is the one whose normal (b - a) x (c - a) points AWAY from the viewer
+        near = g.triangle([0, 0, 0], [0, 2, 0], [2, 0, 0], m)        # prim 0, z = 0, normal (0,0,-4)
+        far = g.triangle([0, 0, -3], [0, 2, -3], [2, 0, -3], m)      # prim 1, z = -3
+        return g.list([near, far])
+    s = scene_from(tmp_path, build)
+    ray = np.array([[0.5, 0.5, 5, 0, 0, -1, 0.0]])
+    try:
+        # the reference: the later triangle replaces the closer hit because Triangle::hit never looks at ray_t
+        ids, t, ex = s.trace_closest(ray, extra=True)
+        assert ids[0] == 1 and t[0] == 8.0
+        np.testing.assert_allclose(ex[0, 6:8], [0.25, 0.25])               # u along c - a, v along b - a
+        np.testing.assert_allclose(ex[0, 3:6], [0, 0, 4])                  # unnormalised (b-a)x(c-a) = (0,0,-4), flipped against the ray
+        # ... and a triangle BEHIND the origin is hit too
+        ids, t = s.trace_closest(np.array([[0.5, 0.5, -1, 0, 0, -1, 0.0]]))
+        assert ids[0] == 1 and t[0] == 2.0
+        ids, t = s.trace_closest(np.array([[0.5, 0.5, -5, 0, 0, -1, 0.0]]))
+        assert ids[0] == 1 and t[0] == -2.0                                # negative t accepted (Q14)
+        # back faces are culled: the same triangles seen from below
+        ids, t = s.trace_closest(np.array([[0.5, 0.5, -9, 0, 0, 1, 0.0]]))
+        assert ids[0] == -1
+        # with the interval applied (the device's rule) the nearest one wins and hits behind the origin vanish
+        orc.set_triangle_interval(True)
+        ids, t = s.trace_closest(ray)
+        assert ids[0] == 0 and t[0] == 5.0
+        ids, t = s.trace_closest(np.array([[0.5, 0.5, -5, 0, 0, -1, 0.0]]))
+        assert ids[0] == -1
+    finally:
+        orc.set_triangle_interval(False)
+
+
+def test_the_reference_triangle_scene_is_insensitive_to_the_interval_bug():
+    """main.rs:836-888 (`triangles`): three triangles forming an open corner.  No camera ray and no scattered ray
+    meets a triangle outside its interval, so the reference's Triangle::hit and the interval-respecting variant the
+    device implements return the same hit for every ray."""
+    s = orc.OracleScene.build("scene10", width=200)
+    rng = np.random.default_rng(2)
+    cam = s.camera_rays(seed=1, sample=0)
+    ids, t, ex = s.trace_closest(cam, extra=True)
+    assert (ids >= 0).mean() > 0.05   # the three triangles cover ~6 % of the view
+    p = np.repeat(ex[ids >= 0, 0:3], 4, axis=0)
+    n = np.repeat(ex[ids >= 0, 3:6], 4, axis=0)
+    d = rng.normal(size=p.shape)
+    # scattered rays as the scene's Lambertian materials produce them: in the hemisphere of the normal that faces the
+    # incoming ray (a ray sent THROUGH its own triangle would re-hit it at t = 0 in the reference: t_min is ignored)
+    d = np.where(((d * n).sum(1) < 0)[:, None], -d, d)
+    rays = np.concatenate([cam, np.concatenate([p, d, np.zeros((p.shape[0], 1))], 1)])
+    a = s.trace_closest(rays)
+    try:
+        orc.set_triangle_interval(True)
+        b = s.trace_closest(rays)
+    finally:
+        orc.set_triangle_interval(False)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
