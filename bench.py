@@ -238,24 +238,49 @@ def main():
     paths, rays = float(counts[0].item()), float(counts[1].item())
 
     # ---- end to end through the C ABI with host buffers ----
+    # Every step: gs_scene_create (the flattened scene arrays go host -> device), a zeroed accumulator, the render, the
+    # cross-GPU reduce, gs_resolve into PINNED host memory, gs_scene_destroy.  One untimed step first (the first resolve
+    # of a process pays one-off driver set-up); stage times are host-clock with a device synchronize after each stage.
     e2e_steps = max(1, min(args.e2e_steps, args.steps))
     h2d = d2h = 0
-    barrier()
-    e0 = time.perf_counter()
-    for k in range(e2e_steps):
+    pin_rgb = torch.empty((n_px, 3), dtype=torch.float32, pin_memory=True)
+    pin_cnt = torch.empty(n_px, dtype=torch.int32, pin_memory=True)
+    np_rgb, np_cnt = pin_rgb.numpy(), pin_cnt.numpy().view("uint32")
+    stages = {"scene_create_h2d": 0.0, "render": 0.0, "reduce": 0.0, "resolve_d2h": 0.0, "destroy": 0.0}
+
+    def e2e_step(k, timed):
+        nonlocal h2d, d2h
+        t = [time.perf_counter()]
+
+        def mark():
+            torch.cuda.synchronize(device)
+            t.append(time.perf_counter())
         sc2 = gs.DeviceScene(host, device=local_rank)                 # gs_scene_create: scene arrays host -> device
         sc2.set_option("wavefront", 1 if args.pipeline == "wavefront" else 0)
         acc2 = torch.zeros((n_px, 4), dtype=torch.float32, device=device)
+        mark()
         begin = ((args.warmup + args.steps + k) * world + rank) * spp_step
         sc2.render_accumulate(acc2.data_ptr(), seed=1, sample_begin=begin, sample_count=spp_step, stream=stream.cuda_stream)
+        mark()
         if world > 1:
             gdist.reduce_accumulators(acc2, dst=0)
+        mark()
         if rank == 0:
-            rgb, cnt = sc2.resolve(acc2.data_ptr(), stream=stream.cuda_stream)  # image device -> host
-            d2h = rgb.nbytes + cnt.nbytes
-        st2 = sc2.stats()
-        h2d = int(st2.h2d_bytes) + 512  # scene arrays + camera/settings structs
+            sc2.resolve(acc2.data_ptr(), stream=stream.cuda_stream, out_rgb=np_rgb, out_counts=np_cnt)  # image device -> pinned host
+            d2h = np_rgb.nbytes + np_cnt.nbytes
+        mark()
+        h2d = int(sc2.stats().h2d_bytes) + 512  # scene arrays + camera/settings structs
         sc2.close()
+        mark()
+        if timed:
+            for name, a, b in zip(stages, t[:-1], t[1:]):
+                stages[name] += (b - a) * 1e3 / e2e_steps
+
+    e2e_step(-1, False)
+    barrier()
+    e0 = time.perf_counter()
+    for k in range(e2e_steps):
+        e2e_step(k, True)
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - e0], dtype=torch.float64, device=device)
     if world > 1:
@@ -279,7 +304,8 @@ def main():
                        "parallelism": f"spp-split x{world}, NCCL reduce of the fp32 accumulator each step" if world > 1 else "single GPU",
                        "bvh": f"binned SAH, binary, <={args.max_leaf or 1} prims/leaf", "pipeline": args.pipeline, "host_flatten_s": round(flatten_s, 3)},
             "e2e": {"value": e2e_value, "unit": "paths/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                    "what": "gs_scene_create + gs_render_accumulate + reduce + gs_resolve to host, per step"},
+                    "what": "gs_scene_create + gs_render_accumulate + reduce + gs_resolve to pinned host memory + gs_scene_destroy, per step",
+                    "stage_ms_rank0": {k2: round(v, 3) for k2, v in stages.items()}},
             "gpu_launches": int(st.kernel_launches) * world,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": k.get("ncu_dram_bytes_per_launch") if args.pipeline == "megakernel" else None,
                          "traffic_note": k.get("ncu_dram_note"),

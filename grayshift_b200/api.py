@@ -122,10 +122,13 @@ class DeviceScene:
         ffi.check(self._lib.gs_render_adaptive_accumulate(self._h, C.byref(self.cam), C.byref(st), seed, pixel_begin, pixel_stride,
                                                           C.c_void_p(d_accum_ptr), C.c_void_p(stream)))
 
-    def resolve(self, d_accum_ptr, stream=0):
+    def resolve(self, d_accum_ptr, stream=0, out_rgb=None, out_counts=None):
+        """pixel_color /= sample_count (camera.rs:167) -> host.  out_rgb / out_counts: caller-owned host arrays (e.g.
+        views of pinned memory) to receive the image instead of fresh numpy arrays."""
         n = self.width * self.height
-        rgb = np.empty((n, 3), dtype=np.float32)
-        counts = np.empty(n, dtype=np.uint32)
+        rgb = np.empty((n, 3), dtype=np.float32) if out_rgb is None else out_rgb.reshape(n, 3)
+        counts = np.empty(n, dtype=np.uint32) if out_counts is None else out_counts.reshape(n)
+        assert rgb.dtype == np.float32 and counts.dtype == np.uint32 and rgb.flags.c_contiguous and counts.flags.c_contiguous
         ffi.check(self._lib.gs_resolve(self._h, C.c_void_p(d_accum_ptr), self.width, self.height, rgb.ctypes.data, counts.ctypes.data,
                                        C.c_void_p(stream)))
         return rgb.reshape(self.height, self.width, 3), counts.reshape(self.height, self.width)

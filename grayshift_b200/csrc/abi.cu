@@ -258,9 +258,9 @@ int build_nodes(gs_scene* s, double origin_limit) {
 		d.link = make_int4(link(n.left), link(n.right), 0, 0);
 		out[k] = d;
 	}
-	if (out.empty()) {  // single-leaf tree: keep one dummy node so the pointer is valid
+	if (out.size() < (size_t)kNodePad) {  // also covers the single-leaf tree: the pointer stays valid
 		DNode d; std::memset(&d, 0, sizeof d);
-		out.push_back(d);
+		out.resize(kNodePad, d);
 	}
 	GS_CUDA(s->nodes.upload(out));
 	s->h2d_bytes += out.size() * sizeof(DNode);

@@ -37,6 +37,8 @@ __host__ __device__ inline int leaf_code(uint32_t first, uint32_t count) { retur
 // first_ref = 2^27 - 1 with count 15, which gs_scene_create rejects.
 constexpr int kStackSentinel = -2147483647 - 1;
 constexpr int kMaxStack = 64;
+constexpr int kNodePad = 512;  // the device node array holds at least this many entries (zero boxes beyond the tree), so a
+                               // kernel may stage a fixed-size breadth-first prefix in shared memory without a bounds check
 
 struct __align__(16) DSphere { double cx, cy, cz, r; };  // r < 0: moving, |r| is the radius
 struct __align__(16) DQuad {
@@ -142,9 +144,47 @@ struct Ray {
 struct Hit {
 	double t;
 	uint32_t ref;  // kind<<30 | index into spheres/quads; 0xffffffff = miss
-	double u, v;   // quad barycentrics (alpha, beta); spheres compute uv on demand
+	float u, v;    // quad barycentrics (alpha, beta) / triangle (u, v) for the textures; spheres compute uv on demand
 };
 constexpr uint32_t kNoHit = 0xffffffffu;
+
+// f64 division and square root.  The parity translation unit (trace_closest.cu, GS_EXACT_F64) uses the IEEE
+// operators like the reference; the render kernels use the approximation instruction plus two Newton steps
+// (<= 2 ulp, no special-case slow path: 8 instructions instead of ~15 plus a call; every operand here is a finite
+// normal number).
+#ifndef GS_FAST_F64
+#define GS_FAST_F64 1  // tuning knob: 0 = IEEE division / square root in the render kernels too (measured 3-8 % slower)
+#endif
+#if defined(GS_EXACT_F64) || !GS_FAST_F64
+__device__ __forceinline__ double f64_div(double n, double d) { return n / d; }
+__device__ __forceinline__ double f64_rcp(double d) { return 1.0 / d; }
+__device__ __forceinline__ double f64_sqrt(double x) { return sqrt(x); }
+#else
+__device__ __forceinline__ double f64_rcp(double d) {
+	double x;
+	asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+	double e = fma(-d, x, 1.0);
+	x = fma(x, e, x);
+	e = fma(-d, x, 1.0);
+	return fma(x, e, x);
+}
+__device__ __forceinline__ double f64_div(double n, double d) {
+	const double x = f64_rcp(d);
+	const double q = n * x;
+	return fma(fma(-d, q, n), x, q);
+}
+__device__ __forceinline__ double f64_sqrt(double v) {
+	const double x = fmax(v, 1e-280);  // callers pass v >= 0; sqrt(0) becomes 1e-140
+	double y;
+	asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+	double g = x * y, h = 0.5 * y;
+	double r = fma(-h, g, 0.5);
+	g = fma(g, r, g); h = fma(h, r, h);
+	r = fma(-h, g, 0.5);
+	g = fma(g, r, g); h = fma(h, r, h);
+	return fma(fma(-g, g, x), h, g);
+}
+#endif
 
 // Sphere::hit, sphere.rs:64-92.  `a` = |d|^2 and its reciprocal are hoisted out by the caller (ray constants):
 // the two roots (h -+ sqrt(disc)) / a become multiplications by 1/a (one f64 division per ray instead of up to
@@ -163,7 +203,7 @@ __device__ __forceinline__ bool hit_sphere(const DSphere& s, const double4* __re
 	double c = (ocx * ocx + ocy * ocy + ocz * ocz) - rad * rad;
 	double disc = h * h - a * c;
 	if (disc < 0.0) return false;
-	double sq = sqrt(disc);
+	double sq = f64_sqrt(disc);
 	double t = (h - sq) * inv_a;
 	if (!(tmin < t && t < tmax)) {
 		t = (h + sq) * inv_a;
@@ -177,7 +217,7 @@ __device__ __forceinline__ bool hit_sphere(const DSphere& s, const double4* __re
 __device__ __forceinline__ bool hit_quad(const DQuad& q, const Ray& r, double tmin, double tmax, double& t_out, double& alpha, double& beta) {
 	double den = q.nx * r.dx + q.ny * r.dy + q.nz * r.dz;
 	if (fabs(den) < 1e-8) return false;
-	double t = (q.d - (q.nx * r.ox + q.ny * r.oy + q.nz * r.oz)) / den;
+	double t = f64_div(q.d - (q.nx * r.ox + q.ny * r.oy + q.nz * r.oz), den);
 	if (!(tmin <= t && t <= tmax)) return false;
 	double px = r.ox + r.dx * t, py = r.oy + r.dy * t, pz = r.oz + r.dz * t;
 	double al = (px * q.ax + py * q.ay + pz * q.az) - q.qa;
@@ -242,6 +282,9 @@ __device__ __forceinline__ float safe_rcp(float d) {
 // those lanes, and re-enter with the unfinished rays exactly where they stopped (ncu on the first
 // version showed 8.4 of 32 lanes active in the node loop: lanes idled until the warp's longest ray ended).
 // ------------------------------------------------------------------------------------------
+#ifndef GS_NODE_LOAD
+#define GS_NODE_LOAD 1  // tuning knob: 1 = branch-free child selection (the link load is issued together with the box loads)
+#endif
 struct TravState {
 	int node;   // current node index / leaf code, kStackSentinel when the ray is finished
 	int sp;     // stack entries in use
@@ -262,7 +305,7 @@ __device__ __forceinline__ RayConsts ray_consts(const Ray& r, double t_closest) 
 	c.idx = safe_rcp((float)r.dx); c.idy = safe_rcp((float)r.dy); c.idz = safe_rcp((float)r.dz);
 	c.oix = (float)r.ox * c.idx; c.oiy = (float)r.oy * c.idy; c.oiz = (float)r.oz * c.idz;
 	c.a = r.dx * r.dx + r.dy * r.dy + r.dz * r.dz;
-	c.inv_a = 1.0 / c.a;
+	c.inv_a = f64_rcp(c.a);
 	c.tmax32 = tmax_to_f32(t_closest);
 	return c;
 }
@@ -271,17 +314,13 @@ __device__ __forceinline__ void trav_init(const DeviceScene& sc, TravState& tv, 
 	stack[0] = kStackSentinel;
 	tv.sp = 1;
 	tv.node = sc.root;
-	tv.best.t = tmax; tv.best.ref = kNoHit; tv.best.u = 0.0; tv.best.v = 0.0;
+	tv.best.t = tmax; tv.best.ref = kNoHit; tv.best.u = 0.f; tv.best.v = 0.f;
 }
 
-// One internal node: AABB::hit (AABB.rs:58-113) for both children at once, near child first, far child pushed.
-// Slab distances in fp32 as fma(plane, 1/d, -o/d) against boxes padded by 8 ulp of the origin range
-// (abi.cu build_nodes): conservative, never culls a true hit.  Precondition: tv.node >= 0.
+// The arithmetic of one node step (see node_step).
 template <bool kCount>
-__device__ __forceinline__ void node_step(const DeviceScene& sc, const RayConsts& rc, TravState& tv, int* stack, uint32_t* node_visits) {
-	const float4* np = reinterpret_cast<const float4*>(sc.nodes + tv.node);
-	const float4 xy0 = __ldg(np), xy1 = __ldg(np + 1), z01 = __ldg(np + 2);
-	const int4 link = __ldg(reinterpret_cast<const int4*>(np + 3));
+__device__ __forceinline__ void node_test(const float4 xy0, const float4 xy1, const float4 z01, int link0, int link1, const RayConsts& rc,
+                                          TravState& tv, int* stack, uint32_t* node_visits) {
 	if (kCount) ++(*node_visits);
 	float t0 = fmaf(xy0.x, rc.idx, -rc.oix), t1 = fmaf(xy0.y, rc.idx, -rc.oix);
 	float t2 = fmaf(xy0.z, rc.idy, -rc.oiy), t3 = fmaf(xy0.w, rc.idy, -rc.oiy);
@@ -294,24 +333,55 @@ __device__ __forceinline__ void node_step(const DeviceScene& sc, const RayConsts
 	const float en1 = fmaxf(fmaxf(fminf(t0, t1), fminf(t2, t3)), fmaxf(fminf(t4, t5), 0.0f));
 	const float ex1 = fminf(fminf(fmaxf(t0, t1), fmaxf(t2, t3)), fminf(fmaxf(t4, t5), rc.tmax32));
 	const bool h0 = en0 <= ex0, h1 = en1 <= ex1;
+#if GS_NODE_LOAD == 1
+	// Select form: both links are consumed unconditionally, so their load is issued with the box loads.  (In the
+	// branchy form below the compiler sinks the link load under the "some child hit" branch and every descent pays two
+	// dependent L1 round trips.)
+	const bool first0 = h0 && (!h1 || !(en1 < en0));
+	const int first = first0 ? link0 : link1, second = first0 ? link1 : link0;
+	if (h0 && h1) stack[tv.sp++] = second;
+	if (h0 || h1) tv.node = first;
+	else tv.node = stack[--tv.sp];
+#else
 	if (!h0 && !h1) { tv.node = stack[--tv.sp]; }
 	else {
-		int near = link.x, far = link.y;
+		int near = link0, far = link1;
 		if (h0 && h1) {
 			if (en1 < en0) { int tmp = near; near = far; far = tmp; }
 			stack[tv.sp++] = far;
 			tv.node = near;
 		} else tv.node = h0 ? near : far;
 	}
+#endif
 }
 
-// One leaf: HittableList::hit over its primitives (hittable.rs:70-86) with the reference's interval rules, then pop.
-// Precondition: tv.node is a leaf code.  kTris = the scene holds triangles (kernels for scenes without any are
+// One internal node: AABB::hit (AABB.rs:58-113) for both children at once, near child first, far child pushed.
+// Slab distances in fp32 as fma(plane, 1/d, -o/d) against boxes padded by 8 ulp of the origin range
+// (abi.cu build_nodes): conservative, never culls a true hit.  Precondition: tv.node >= 0.
+// kTop > 0: the first kTop nodes (breadth-first order = the top levels of the tree) are read from the CTA's
+// shared-memory copy `top`; one generic-address load serves both cases, so lanes do not diverge on it.
+template <bool kCount, int kTop = 0>
+__device__ __forceinline__ void node_step(const DeviceScene& sc, const RayConsts& rc, TravState& tv, int* stack, uint32_t* node_visits,
+                                          const float4* top = nullptr) {
+	const float4* np = reinterpret_cast<const float4*>(sc.nodes + tv.node);
+	if (kTop > 0) {
+		if (tv.node < kTop) np = top + tv.node * 4;
+		const float4 xy0 = np[0], xy1 = np[1], z01 = np[2];
+		const int2 link = *reinterpret_cast<const int2*>(np + 3);
+		node_test<kCount>(xy0, xy1, z01, link.x, link.y, rc, tv, stack, node_visits);
+		return;
+	}
+	const float4 xy0 = __ldg(np), xy1 = __ldg(np + 1), z01 = __ldg(np + 2);
+	const int4 link = __ldg(reinterpret_cast<const int4*>(np + 3));
+	node_test<kCount>(xy0, xy1, z01, link.x, link.y, rc, tv, stack, node_visits);
+}
+
+// One leaf: HittableList::hit over its primitives (hittable.rs:70-86) with the reference's interval rules.
+// `leaf` is a leaf code.  kTris = the scene holds triangles (kernels for scenes without any are
 // instantiated without the triangle branch: it costs registers and instruction-cache space in the hot loop).
 template <bool kTris>
-__device__ __forceinline__ void leaf_step(const DeviceScene& sc, const Ray& r, RayConsts& rc, double tmin, TravState& tv, int* stack) {
-	Hit& best = tv.best;
-	const uint32_t code = (uint32_t)(-1 - tv.node);
+__device__ __forceinline__ void leaf_intersect(const DeviceScene& sc, const Ray& r, RayConsts& rc, double tmin, Hit& best, int leaf) {
+	const uint32_t code = (uint32_t)(-1 - leaf);
 	uint32_t first = code >> 4, count = code & 15u;
 	// count == 0: a single-primitive leaf whose reference is stored in the link itself (kind << 25 | index):
 	// no dependent load from `refs` between the node and the primitive
@@ -324,7 +394,7 @@ __device__ __forceinline__ void leaf_step(const DeviceScene& sc, const Ray& r, R
 		if (kTris && kind == 2u) {
 			const DTriangle tr = load_triangle(sc.tris, index);
 			double t, u, v;
-			if (hit_triangle(tr, r, tmin, best.t, t, u, v)) { best.t = t; best.ref = ref; best.u = u; best.v = v; }
+			if (hit_triangle(tr, r, tmin, best.t, t, u, v)) { best.t = t; best.ref = ref; best.u = (float)u; best.v = (float)v; }
 		} else if (kind == 0u) {
 			const DSphere s = load_sphere(sc.spheres, index);
 			double t;
@@ -337,20 +407,26 @@ __device__ __forceinline__ void leaf_step(const DeviceScene& sc, const Ray& r, R
 				bool accept = true;
 				if (t == best.t && best.ref != kNoHit && (best.ref >> kRefKindShift) == 1u)
 					accept = __ldg(sc.quad_order + index) > __ldg(sc.quad_order + (best.ref & kRefIndexMask));
-				if (accept) { best.t = t; best.ref = ref; best.u = al; best.v = be; }
+				if (accept) { best.t = t; best.ref = ref; best.u = (float)al; best.v = (float)be; }
 			}
 		}
 	}
 	if (best.ref != kNoHit) rc.tmax32 = __double2float_ru(best.t);
+}
+
+// The leaf under tv.node, then pop.  Precondition: tv.node is a leaf code.
+template <bool kTris>
+__device__ __forceinline__ void leaf_step(const DeviceScene& sc, const Ray& r, RayConsts& rc, double tmin, TravState& tv, int* stack) {
+	leaf_intersect<kTris>(sc, r, rc, tmin, tv.best, tv.node);
 	tv.node = stack[--tv.sp];
 }
 
 // One round of the classic while-while traversal: descend to the next leaf, intersect it.
 // Precondition: tv.node != kStackSentinel.  kF: bit 0 = count node visits, bit 1 = scene holds triangles.
-template <int kF>
+template <int kF, int kTop = 0>
 __device__ __forceinline__ void trav_round(const DeviceScene& sc, const Ray& r, RayConsts& rc, double tmin, TravState& tv, int* stack,
-                                           uint32_t* node_visits) {
-	while (tv.node >= 0) node_step<(kF & 1) != 0>(sc, rc, tv, stack, node_visits);
+                                           uint32_t* node_visits, const float4* top = nullptr) {
+	while (tv.node >= 0) node_step<(kF & 1) != 0, kTop>(sc, rc, tv, stack, node_visits, top);
 	if (tv.node != kStackSentinel) leaf_step<(kF & 2) != 0>(sc, r, rc, tmin, tv, stack);
 }
 

@@ -282,7 +282,7 @@ __device__ __forceinline__ bool medium_event(const DeviceScene& sc, const DMediu
 		double c = (ocx * ocx + ocy * ocy + ocz * ocz) - rad * rad;
 		double disc = h * h - a * c;
 		if (disc < 0.0) return false;
-		double sq = sqrt(disc);
+		double sq = f64_sqrt(disc);
 		t1 = (h - sq) * inv_a;
 		t2 = (h + sq) * inv_a;
 		if (!(t1 > -kMax && t1 < kMax)) return false;
@@ -312,12 +312,11 @@ struct PathState {
 	f3 L, T;
 	PathRng rng;
 	unsigned bounce;
-	uint32_t pixel;
+	__device__ __forceinline__ uint32_t pixel() const { return rng.pixel; }
 };
 
 __device__ __forceinline__ void path_begin(PathState& st, const DCamera& cam, uint64_t seed, uint32_t pixel, uint32_t sample) {
 	st.rng.start(seed, pixel, sample);
-	st.pixel = pixel;
 	st.ray = get_ray(cam, (int)(pixel % (uint32_t)cam.width), (int)(pixel / (uint32_t)cam.width), st.rng);
 	st.L = mk3(0.f, 0.f, 0.f);
 	st.T = mk3(1.f, 1.f, 1.f);
@@ -335,8 +334,9 @@ __device__ __forceinline__ bool segment_begin(const DeviceScene& sc, const DCame
 	if (sc.n_media > 0) {
 		const Ray& ray = st.ray;
 		const double a = ray.dx * ray.dx + ray.dy * ray.dy + ray.dz * ray.dz;
-		const double inv_a = 1.0 / a;
-		// media stream: counter word 3 = 1, block = bounce * 64 + group, 4 media per block
+		const double inv_a = f64_rcp(a);
+		// media stream: counter word 3 = 1, block = bounce * 64 + group, 4 media per block.  (Drawing from the path's own
+		// stream instead saves one Philox block per level: measured +1 % on C4, not worth a second draw order.)
 		uint4 blk = make_uint4(0u, 0u, 0u, 0u);
 		for (int mi = 0; mi < sc.n_media; ++mi) {
 			if ((mi & 3) == 0) blk = philox4x32_10(st.rng.pixel, st.rng.sample, st.bounce * 64u + (uint32_t)(mi >> 2), 1u, st.rng.k0, st.rng.k1);
@@ -371,7 +371,7 @@ __device__ __forceinline__ bool segment_shade(const DeviceScene& sc, const DCame
 			// normalises it in its ONB; Metal and Dielectric reflect about it as it is)
 			const DTriangle tr = load_triangle(sc.tris, index);
 			n_out = mk3((float)(tr.e2y * tr.e1z - tr.e2z * tr.e1y), (float)(tr.e2z * tr.e1x - tr.e2x * tr.e1z), (float)(tr.e2x * tr.e1y - tr.e2y * tr.e1x));
-			s.is_sphere = false; s.u = (float)h.u; s.v = (float)h.v;
+			s.is_sphere = false; s.u = h.u; s.v = h.v;
 			s.material = __ldg(sc.tri_aux + index).x;
 		} else if ((h.ref >> kRefKindShift) == 0u) {
 			DSphere sp = load_sphere(sc.spheres, index);
@@ -385,7 +385,7 @@ __device__ __forceinline__ bool segment_shade(const DeviceScene& sc, const DCame
 			const double2* qp = reinterpret_cast<const double2*>(sc.quads + index);
 			double2 n01 = __ldg(qp), n23 = __ldg(qp + 1);
 			n_out = mk3((float)n01.x, (float)n01.y, (float)n23.x);
-			s.is_sphere = false; s.u = (float)h.u; s.v = (float)h.v;
+			s.is_sphere = false; s.u = h.u; s.v = h.v;
 			s.material = __ldg(sc.quad_aux + index).x;
 		}
 	} else {  // medium event: normal (1,0,0), u = v = 0, phase function as the material (volume.rs:54-62, Q10)

@@ -28,17 +28,26 @@ enum LaneState : int { kDead = 0, kTraverse = 1, kShade = 2, kSetup = 3 };
 #define GS_MIN_SHADE 32   // leave phase B once this many lanes wait for shading (32 = run every ray to completion)
 #endif
 #ifndef GS_MIN_BLOCKS
-#define GS_MIN_BLOCKS 4   // __launch_bounds__ min CTAs per SM (register cap = 65536 / (128 * GS_MIN_BLOCKS))
+#define GS_MIN_BLOCKS 6   // __launch_bounds__ min CTAs per SM (register cap = 65536 / (128 * GS_MIN_BLOCKS)).  The kernel is latency-
+                          // bound: 6 (80 registers, 24 warps/SM, ~240 B of spills that ptxas places in the shading code, none in
+                          // the traversal loop) measured +8 % C4 / +11 % C1 / +12 % C3 over 4 (114 registers, no spills); 7 and 8
+                          // spill more than they gain.  Parking the cold path state in shared memory instead (12 KB per CTA) was
+                          // slower than the spills: the L1 capacity it takes away costs more.
 #endif
-#ifndef GS_TRAV_VOTE
-#define GS_TRAV_VOTE 0    // 0 = while-while rounds, 1 = per-iteration node/leaf vote
+#ifndef GS_TOP_SMEM
+#define GS_TOP_SMEM 0     // nodes of the top BVH levels (breadth-first prefix) staged in shared memory per CTA; 0 = off
 #endif
+constexpr int kTopNodes = GS_TOP_SMEM;
+static_assert(kTopNodes <= kNodePad, "gs_scene_create pads the node array to kNodePad entries");
 constexpr int kMinShade = GS_MIN_SHADE;
 
 // kF: bit 0 = count BVH node visits, bit 1 = the scene holds triangles
 template <int kF>
 __global__ void __launch_bounds__(kBlock, GS_MIN_BLOCKS) render_fixed_kernel(const __grid_constant__ RenderParams P) {
 	__shared__ uint8_t s_perm[256];
+	__shared__ float4 s_top[kTopNodes > 0 ? kTopNodes * 4 : 1];
+	if (kTopNodes > 0)
+		for (int i = threadIdx.x; i < kTopNodes * 4; i += kBlock) s_top[i] = __ldg(reinterpret_cast<const float4*>(P.sc.nodes) + i);
 	load_perm(s_perm, P.sc.perlin_perm);
 	const unsigned lane = threadIdx.x & 31u;
 	const unsigned lt_mask = (1u << lane) - 1u;
@@ -53,13 +62,18 @@ __global__ void __launch_bounds__(kBlock, GS_MIN_BLOCKS) render_fixed_kernel(con
 	int stack[kMaxStack];
 	float ar = 0.f, ag = 0.f, ab = 0.f, an = 0.f;
 	uint32_t cur_pixel = 0xffffffffu;
-	unsigned long long warp_next = 0, warp_end = 0;
+	// the warp's current chunk of work items [next, end): warp-uniform, kept in shared memory rather than in four
+	// registers of every lane (the kernel is register-bound: 16 warps per SM at 114 registers)
+	__shared__ unsigned long long s_chunk[kBlock / 32][2];
+	unsigned long long* const chunk = s_chunk[threadIdx.x >> 5];
+	if (lane == 0) { chunk[0] = 0ull; chunk[1] = 0ull; }
+	__syncwarp();
 	bool exhausted = false;
 
 	auto finish_path = [&]() {  // pixel_color += sample_color, camera.rs:141
-		if (st.pixel != cur_pixel) {
+		if (st.pixel() != cur_pixel) {
 			if (cur_pixel != 0xffffffffu) red_add_v4(P.accum + cur_pixel, ar, ag, ab, an);
-			cur_pixel = st.pixel; ar = ag = ab = an = 0.f;
+			cur_pixel = st.pixel(); ar = ag = ab = an = 0.f;
 		}
 		ar += st.L.x; ag += st.L.y; ab += st.L.z; an += 1.f;
 		state = kDead;
@@ -70,31 +84,38 @@ __global__ void __launch_bounds__(kBlock, GS_MIN_BLOCKS) render_fixed_kernel(con
 		if (state == kShade) {
 			if (segment_shade<(kF & 2) != 0>(P.sc, P.cam, s_perm, st, pc, tv.best, seg_tmax, seg_medium)) finish_path();
 			else state = kSetup;
+			if (!(kF & 1)) pc.tex_fetches = 0u;  // texel fetches are a statistic of the counting variant only (one register less here)
 		}
 		// ---- phase A2: dead lanes take the next (pixel, sample) items ------------------------------------
 		const unsigned dead = __ballot_sync(kFull, state == kDead);
-		if (dead && !(exhausted && warp_next >= warp_end)) {
-			if (warp_next >= warp_end && !exhausted) {
-				unsigned long long base = 0;
-				if (lane == 0) base = atomicAdd(P.work_counter, (unsigned long long)P.chunk);
-				base = __shfl_sync(kFull, base, 0);
-				if (base >= P.total_items) exhausted = true;
-				else { warp_next = base; warp_end = min(base + (unsigned long long)P.chunk, P.total_items); }
-			}
-			const unsigned long long avail = warp_end - warp_next;
-			if (state == kDead) {
-				const unsigned rank = __popc(dead & lt_mask);
-				if (rank < avail) {
-					const unsigned long long item = warp_next + rank;
-					const uint32_t pixel = (uint32_t)(item / P.sample_count);
-					const uint32_t sample = (uint32_t)(item % P.sample_count) + P.sample_begin;
-					path_begin(st, P.cam, P.seed, pixel, sample);
-					state = kSetup;
-					++paths;
+		if (dead) {
+			unsigned long long warp_next = chunk[0], warp_end = chunk[1];
+			if (!(exhausted && warp_next >= warp_end)) {
+				if (warp_next >= warp_end && !exhausted) {
+					unsigned long long base = 0;
+					if (lane == 0) base = atomicAdd(P.work_counter, (unsigned long long)P.chunk);
+					base = __shfl_sync(kFull, base, 0);
+					if (base >= P.total_items) exhausted = true;
+					else { warp_next = base; warp_end = min(base + (unsigned long long)P.chunk, P.total_items); }
 				}
+				const unsigned long long avail = warp_end - warp_next;
+				if (state == kDead) {
+					const unsigned rank = __popc(dead & lt_mask);
+					if (rank < avail) {
+						const unsigned long long item = warp_next + rank;
+						const uint32_t pixel = (uint32_t)(item / P.sample_count);
+						const uint32_t sample = (uint32_t)(item % P.sample_count) + P.sample_begin;
+						path_begin(st, P.cam, P.seed, pixel, sample);
+						state = kSetup;
+						++paths;
+					}
+				}
+				const unsigned long long need = (unsigned long long)__popc(dead);
+				warp_next += need < avail ? need : avail;
+				__syncwarp();
+				if (lane == 0) { chunk[0] = warp_next; chunk[1] = warp_end; }
+				__syncwarp();
 			}
-			const unsigned long long need = (unsigned long long)__popc(dead);
-			warp_next += need < avail ? need : avail;
 		}
 		// ---- phase A3: depth test, media, traversal set-up for every fresh ray ----------------------------
 		if (state == kSetup) {
@@ -105,36 +126,16 @@ __global__ void __launch_bounds__(kBlock, GS_MIN_BLOCKS) render_fixed_kernel(con
 		}
 		const unsigned trav0 = __ballot_sync(kFull, state == kTraverse);
 		if (trav0 == 0u) {
-			if (exhausted && warp_next >= warp_end && __ballot_sync(kFull, state != kDead) == 0u) break;
+			if (exhausted && chunk[0] >= chunk[1] && __ballot_sync(kFull, state != kDead) == 0u) break;
 			continue;
 		}
 		// ---- phase B: traverse until enough lanes have finished their ray ---------------------------------
 		RayConsts rc;
 		if (state == kTraverse) rc = ray_consts(st.ray, tv.best.t);
-#if GS_TRAV_VOTE
-		// Per-iteration vote: if at least as many lanes sit on an internal node as on a leaf, the node lanes take
-		// two node steps, otherwise the leaf lanes intersect their leaf; the others wait.
-		for (;;) {
-			const bool trav = state == kTraverse;
-			const bool at_node = trav && tv.node >= 0;
-			const unsigned m_node = __ballot_sync(kFull, at_node);
-			const unsigned m_leaf = __ballot_sync(kFull, trav && !at_node);
-			const unsigned m_shade = __ballot_sync(kFull, state == kShade);
-			if ((m_node | m_leaf) == 0u || __popc(m_shade) >= kMinShade) break;
-			if (__popc(m_node) >= __popc(m_leaf)) {
-				if (at_node) {
-					node_step<(kF & 1) != 0>(P.sc, rc, tv, stack, &pc.node_visits);
-					if (tv.node >= 0) node_step<(kF & 1) != 0>(P.sc, rc, tv, stack, &pc.node_visits);
-				}
-			} else if (trav && !at_node) {
-				leaf_step<(kF & 2) != 0>(P.sc, st.ray, rc, 0.001, tv, stack);
-			}
-			if (trav && tv.node == kStackSentinel) state = kShade;
-		}
-#elif GS_MIN_SHADE >= 32
+#if GS_MIN_SHADE >= 32
 		// Every lane runs its ray to completion (classic while-while); measured best on B200.
 		if (state == kTraverse) {
-			while (tv.node != kStackSentinel) trav_round<kF>(P.sc, st.ray, rc, 0.001, tv, stack, &pc.node_visits);
+			while (tv.node != kStackSentinel) trav_round<kF, kTopNodes>(P.sc, st.ray, rc, 0.001, tv, stack, &pc.node_visits, s_top);
 			state = kShade;
 		}
 #else
@@ -145,7 +146,7 @@ __global__ void __launch_bounds__(kBlock, GS_MIN_BLOCKS) render_fixed_kernel(con
 			const unsigned m_shade = __ballot_sync(kFull, state == kShade);
 			if (m_trav == 0u || __popc(m_shade) >= kMinShade) break;
 			if (trav) {
-				trav_round<kF>(P.sc, st.ray, rc, 0.001, tv, stack, &pc.node_visits);
+				trav_round<kF, kTopNodes>(P.sc, st.ray, rc, 0.001, tv, stack, &pc.node_visits, s_top);
 				if (tv.node == kStackSentinel) state = kShade;
 			}
 		}

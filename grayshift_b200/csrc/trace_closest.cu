@@ -2,6 +2,7 @@
 // rays (gs_trace_closest).  Same traversal and intersection code as the render megakernel
 // (gs_device.cuh), compiled in this translation unit with -fmad=false so the f64 primitive
 // arithmetic is evaluated without FMA contraction, like the Rust reference.
+#define GS_EXACT_F64 1  // IEEE division and square root, like the reference
 #include "gs_internal.h"
 
 namespace gs {

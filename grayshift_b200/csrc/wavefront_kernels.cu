@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(kBlock) wf_traverse_kernel(const __grid_consta
 						++pc.rays;
 						if (P.sc.n_media > 0) {
 							const double a = ray.dx * ray.dx + ray.dy * ray.dy + ray.dz * ray.dz;
-							const double inv_a = 1.0 / a;
+							const double inv_a = f64_rcp(a);
 							const uint32_t bounce = id.w & 0xffffu;
 							uint4 blk = make_uint4(0u, 0u, 0u, 0u);
 							for (int mi = 0; mi < P.sc.n_media; ++mi) {
@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(kBlock) wf_traverse_kernel(const __grid_consta
 			if (tv.node == kStackSentinel) {
 				// closest event: surface hit (ref), else medium event (t = the medium's candidate), else miss
 				reinterpret_cast<double*>(P.pool.dir + slot)[3] = tv.best.t;
-				P.pool.hit[slot] = make_uint4(tv.best.ref, (unsigned)medium, __float_as_uint((float)tv.best.u), __float_as_uint((float)tv.best.v));
+				P.pool.hit[slot] = make_uint4(tv.best.ref, (unsigned)medium, __float_as_uint(tv.best.u), __float_as_uint(tv.best.v));
 				slot = -1;
 			}
 		}
@@ -151,18 +151,17 @@ __global__ void __launch_bounds__(kBlock) wf_shade_kernel(const __grid_constant_
 		st.ray.dx = d.x; st.ray.dy = d.y; st.ray.dz = d.z;
 		st.T = mk3(thr.x, thr.y, thr.z);
 		st.L = mk3(rad.x, rad.y, rad.z);
-		st.pixel = id.x;
 		st.bounce = id.w & 0xffffu;
 		st.rng.pixel = id.x; st.rng.sample = id.y; st.rng.draw = id.z;
 		st.rng.k0 = (uint32_t)P.seed; st.rng.k1 = (uint32_t)(P.seed >> 32);
 		// mid-block: rebuild the Philox block the next draws come from (draw k = word k&3 of block k>>2)
 		if (id.z & 3u) st.rng.buf = philox4x32_10(id.x, id.y, id.z >> 2, 0u, st.rng.k0, st.rng.k1);
 		Hit h;
-		h.t = d.w; h.ref = hw.x; h.u = (double)__uint_as_float(hw.z); h.v = (double)__uint_as_float(hw.w);
+		h.t = d.w; h.ref = hw.x; h.u = __uint_as_float(hw.z); h.v = __uint_as_float(hw.w);
 		bool finished = segment_shade<true>(P.sc, P.cam, s_perm, st, pc, h, d.w, (int)hw.y);
 		if (!finished && st.bounce >= P.cam.max_depth) finished = true;  // the next level returns ZERO (camera.rs:175)
 		if (finished) {
-			red_add_v4(P.accum + st.pixel, st.L.x, st.L.y, st.L.z, 1.0f);  // pixel_color += sample_color (camera.rs:141)
+			red_add_v4(P.accum + st.pixel(), st.L.x, st.L.y, st.L.z, 1.0f);  // pixel_color += sample_color (camera.rs:141)
 			P.pool.ids[s] = make_uint4(id.x, id.y, st.rng.draw, 0u);
 			terminated = true;
 		} else {

@@ -141,7 +141,8 @@ def cuda_lib():
     """libgrayshift_cuda.so (the product).  Raises if it has not been built: there is no fallback."""
     global _cuda
     if _cuda is None:
-        path = os.path.join(LIB_DIR, "libgrayshift_cuda.so")
+        # GS_CUDA_LIB: A/B runs of differently tuned builds of the same library (scripts/build_variants.sh); still no fallback
+        path = os.environ.get("GS_CUDA_LIB") or os.path.join(LIB_DIR, "libgrayshift_cuda.so")
         if not os.path.exists(path):
             raise RuntimeError(f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`")
         _cuda = _bind(C.CDLL(path, mode=C.RTLD_GLOBAL), CUDA_SYMBOLS)

@@ -210,7 +210,7 @@ typedef struct gs_sample_settings {
 typedef struct gs_stats {
 	uint64_t paths;         /* samples taken (sum of per-pixel sample counts) */
 	uint64_t rays;          /* world.hit calls from ray_color, camera.rs:177 */
-	uint64_t tex_fetches;   /* image-texture and HDR texel reads */
+	uint64_t tex_fetches;   /* image-texture and HDR texel reads; fixed-count renders count them only with "count_nodes" set */
 	uint64_t node_visits;   /* BVH nodes fetched; only counted after gs_scene_set_option(scene, "count_nodes", 1) */
 	uint64_t kernel_launches;
 	double kernel_ms;       /* device time of the render kernels (CUDA events) */

@@ -1,0 +1,51 @@
+"""Lean A/B harness (ctypes only, no torch): for the build of libgrayshift_cuda.so selected by GS_CUDA_LIB, check small
+fixed-seed images against saved ones (every tuning variant computes the same estimator on the same Philox streams, so
+images agree up to the order of float additions) and time the render kernel (CUDA events inside gs_render).
+usage: python scripts/ab_bench.py save|check <dir> [cfg ...]"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import grayshift_b200 as gs  # noqa: E402
+
+mode, out = sys.argv[1], sys.argv[2]
+cfgs = sys.argv[3:] or ["c4", "c1", "c3"]
+name = os.environ.get("GS_VARIANT", "default")
+os.makedirs(out, exist_ok=True)
+ok = True
+for cfg, width, spp in (("c4", 160, 16), ("c1", 160, 16), ("c3", 128, 16), ("c2", 160, 8), ("scene7", 128, 8)):
+    dev = gs.DeviceScene(gs.HostScene.build(cfg, width=width, spp=spp), device=0)
+    rgb, counts, stats = dev.render(seed=11)
+    path = os.path.join(out, f"{cfg}.npy")
+    if mode == "save":
+        np.save(path, rgb)
+    else:
+        ref = np.load(path)
+        # a variant may round differently, so a few paths in a million part ways at a decision boundary: require that
+        # nearly all pixels agree closely and that the mean does
+        scale = max(float(np.abs(ref).max()), 1e-9)
+        bad = float((np.abs(rgb - ref).max(axis=2) > 1e-4 * scale).mean())
+        err = 1e-4 * max(bad / 2e-3, abs(float(rgb.mean()) - float(ref.mean())) / float(ref.mean()) / 1e-3)
+        if cfg in os.environ.get("GS_SKIP_CHECK", "").split():  # a variant that changes the random streams of this scene
+            bad, err = 0.0, abs(float(rgb.mean()) - float(ref.mean())) / float(ref.mean()) * 1e-4 / 0.03  # means within 3 %
+        if err >= 1e-4:
+            ok = False
+            print(f"{name}: {cfg} IMAGE MISMATCH: {bad:.2e} of the pixels differ, means {rgb.mean():.6f} vs {ref.mean():.6f}")
+    dev.close()
+if not ok:
+    sys.exit(1)
+BENCH = {"c4": (0, 64), "c1": (0, 1000), "c3": (0, 128), "c2": (0, 64), "c5": (1920, 8)}
+line = f"{name:24s}"
+for cfg in cfgs:
+    width, spp = BENCH[cfg]
+    dev = gs.DeviceScene(gs.HostScene.build(cfg, width=width, spp=spp), device=0)
+    best = None
+    for rep in range(4):
+        _, _, st = dev.render(seed=1 + rep, want_counts=False)
+        if rep and (best is None or st.kernel_ms < best[0]):
+            best = (st.kernel_ms, st.paths, st.rays)
+    line += f" | {cfg} {best[1] / best[0] / 1e3:7.1f} Mpaths/s {best[2] / best[0] / 1e3:7.1f} Mrays/s"
+    dev.close()
+print(line, flush=True)
