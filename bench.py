@@ -80,6 +80,10 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
+        try:
+            self.proc.wait(timeout=3)  # gone before the end-to-end leg starts: its queries take the driver's lock
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
         sm, mx, reasons = [], [], set()
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]

@@ -4,6 +4,8 @@
 // without a CUDA device every compute entry fails with GS_ERR_NO_DEVICE.
 #include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -26,6 +28,28 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
 float float_down(double x) { float f = (float)x; if ((double)f > x) f = std::nextafterf(f, -INFINITY); return f; }
 float float_up(double x) { float f = (float)x; if ((double)f < x) f = std::nextafterf(f, INFINITY); return f; }
 
+// Device memory comes from the device's stream-ordered pool with the release threshold lifted, so creating and
+// destroying scenes reuses the same HBM instead of mapping / unmapping it each time (cudaMalloc + cudaFree of a
+// 2.6 MB scene measured 25 + 55 ms per create/destroy pair next to a 226 ms render; from the pool it is < 1 ms).
+// All pool traffic is ordered on the legacy default stream; gs_scene_create / gs_scene_destroy synchronize the device.
+cudaError_t dev_alloc(void** p, size_t bytes) {
+	static thread_local int tuned_device = -1;
+	int dev = 0;
+	cudaError_t e = cudaGetDevice(&dev);
+	if (e != cudaSuccess) return e;
+	if (tuned_device != dev) {
+		cudaMemPool_t pool;
+		e = cudaDeviceGetDefaultMemPool(&pool, dev);
+		if (e != cudaSuccess) return e;
+		unsigned long long keep = ~0ull;
+		e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+		if (e != cudaSuccess) return e;
+		tuned_device = dev;
+	}
+	return cudaMallocAsync(p, bytes, 0);
+}
+void dev_free(void* p) { if (p) cudaFreeAsync(p, 0); }
+
 template <class T> struct DevBuf {
 	T* p = nullptr;
 	size_t n = 0;
@@ -33,7 +57,7 @@ template <class T> struct DevBuf {
 		release();
 		n = h.size();
 		if (n == 0) return cudaSuccess;
-		cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+		cudaError_t e = dev_alloc(reinterpret_cast<void**>(&p), n * sizeof(T));
 		if (e != cudaSuccess) return e;
 		return cudaMemcpy(p, h.data(), n * sizeof(T), cudaMemcpyHostToDevice);
 	}
@@ -41,12 +65,13 @@ template <class T> struct DevBuf {
 		if (count <= n && p) return cudaSuccess;
 		release();
 		n = count;
-		return cudaMalloc(&p, n * sizeof(T));
+		return dev_alloc(reinterpret_cast<void**>(&p), n * sizeof(T));
 	}
-	void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+	void release() { dev_free(p); p = nullptr; n = 0; }
 };
 
 constexpr int kCounterSlots = 64;
+constexpr int kStatSlots = 16;  // [0..3] = gs_stats totals; [4..] only written by the GS_DIVERGENCE_STATS diagnostic build
 
 }  // namespace
 
@@ -108,7 +133,8 @@ struct gs_scene {
 
 	~gs_scene() {
 		cudaSetDevice(device);
-		for (void* t : image_texels) cudaFree(t);
+		cudaDeviceSynchronize();  // nothing of this scene is in flight when its memory goes back to the pool
+		for (void* t : image_texels) dev_free(t);
 		pool_org.release(); pool_dir.release(); pool_thr.release(); pool_rad.release(); pool_ids.release(); pool_hit.release();
 		free_list.release(); wave_ctr.release();
 		if (h_wave_ctr) cudaFreeHost(h_wave_ctr);
@@ -335,21 +361,35 @@ int gs_device_count(void) {
 int gs_scene_create(const gs_scene_desc* d, int device, gs_scene** out) {
 	if (!out) return fail(GS_ERR_INVALID, "null out pointer");
 	*out = nullptr;
+	// GS_TRACE=1: stage times of this call on stderr (host clock)
+	static const bool trace = std::getenv("GS_TRACE") != nullptr;
+	auto t_prev = std::chrono::steady_clock::now();
+	auto lap = [&](const char* what) {
+		if (!trace) return;
+		auto now = std::chrono::steady_clock::now();
+		std::fprintf(stderr, "[gs_scene_create] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+		t_prev = now;
+	};
 	int rc = validate(d);
+	lap("validate");
 	if (rc) return rc;
 	int ndev = gs_device_count();
 	if (ndev == 0) return fail(GS_ERR_NO_DEVICE, "no CUDA device available (there is no CPU fallback)");
 	if (device < 0 || device >= ndev) return fail(GS_ERR_INVALID, "device ordinal out of range");
 	GS_CUDA(cudaSetDevice(device));
-	cudaDeviceProp prop;
-	GS_CUDA(cudaGetDeviceProperties(&prop, device));
-	if (prop.major < 10) return fail(GS_ERR_UNSUPPORTED, std::string("device '") + prop.name + "' is not sm_100 class; this library carries sm_100a code only");
+	// two attribute queries instead of cudaGetDeviceProperties, which fills in every property of the device and was
+	// the slowest call of a scene creation
+	int cc_major = 0, sm_count = 0;
+	GS_CUDA(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, device));
+	GS_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
+	if (cc_major < 10) return fail(GS_ERR_UNSUPPORTED, "device " + std::to_string(device) + " is not sm_100 class; this library carries sm_100a code only");
 
 	gs_scene* s = new gs_scene();
 	s->device = device;
-	s->sm_count = prop.multiProcessorCount;
+	s->sm_count = sm_count;
 	struct Guard { gs_scene* s; bool ok = false; ~Guard() { if (!ok) delete s; } } guard{s};
 
+	lap("device attributes");
 	// ---- tree walk: BFS numbering of internal nodes, DFS leaf order for the references ----
 	s->h_nodes.assign(d->nodes, d->nodes + d->n_nodes);
 	s->h_node_to_dnode.assign(d->n_nodes, -1);
@@ -437,6 +477,7 @@ int gs_scene_create(const gs_scene_desc* d, int device, gs_scene** out) {
 	}
 	s->max_abs_coord = mx;
 
+	lap("re-layout (host)");
 	// ---- upload ----
 	GS_CUDA(s->refs.upload(refs));
 	GS_CUDA(s->spheres.upload(spheres)); GS_CUDA(s->sph_path.upload(sph_path)); GS_CUDA(s->sph_aux.upload(sph_aux));
@@ -493,7 +534,7 @@ int gs_scene_create(const gs_scene_desc* d, int device, gs_scene** out) {
 				std::vector<uchar4> t(n);
 				const uint8_t* p = static_cast<const uint8_t*>(im.pixels);
 				for (size_t k = 0; k < n; ++k) t[k] = make_uchar4(p[k * 3], p[k * 3 + 1], p[k * 3 + 2], 255);
-				GS_CUDA(cudaMalloc(&dev, n * sizeof(uchar4)));
+				GS_CUDA(dev_alloc(&dev, n * sizeof(uchar4)));
 				s->image_texels.push_back(dev);
 				GS_CUDA(cudaMemcpy(dev, t.data(), n * sizeof(uchar4), cudaMemcpyHostToDevice));
 				s->h2d_bytes += n * sizeof(uchar4);
@@ -501,7 +542,7 @@ int gs_scene_create(const gs_scene_desc* d, int device, gs_scene** out) {
 				std::vector<float4> t(n);
 				const float* p = static_cast<const float*>(im.pixels);
 				for (size_t k = 0; k < n; ++k) t[k] = make_float4(p[k * 3], p[k * 3 + 1], p[k * 3 + 2], 0.f);
-				GS_CUDA(cudaMalloc(&dev, n * sizeof(float4)));
+				GS_CUDA(dev_alloc(&dev, n * sizeof(float4)));
 				s->image_texels.push_back(dev);
 				GS_CUDA(cudaMemcpy(dev, t.data(), n * sizeof(float4), cudaMemcpyHostToDevice));
 				s->h2d_bytes += n * sizeof(float4);
@@ -517,9 +558,10 @@ int gs_scene_create(const gs_scene_desc* d, int device, gs_scene** out) {
 			GS_CUDA(s->perm.upload(pm));
 		}
 	}
+	lap("upload primitives + tables");
 	GS_CUDA(s->counters.alloc(kCounterSlots));
-	GS_CUDA(s->stats.alloc(4));
-	GS_CUDA(cudaMemset(s->stats.p, 0, 4 * sizeof(unsigned long long)));
+	GS_CUDA(s->stats.alloc(kStatSlots));
+	GS_CUDA(cudaMemset(s->stats.p, 0, kStatSlots * sizeof(unsigned long long)));
 
 	DeviceScene& ds = s->ds;
 	ds.refs = s->refs.p; ds.spheres = s->spheres.p; ds.sph_path = s->sph_path.p; ds.sph_aux = s->sph_aux.p;
@@ -532,6 +574,7 @@ int gs_scene_create(const gs_scene_desc* d, int device, gs_scene** out) {
 	ds.root = d->nodes[0].ref_count > 0 ? s->h_leaf_code[0] : 0;
 	rc = build_nodes(s, 4.0 * std::fmax(mx, 1.0));
 	if (rc) return rc;
+	lap("nodes: pad + upload");
 	guard.ok = true;
 	*out = s;
 	return GS_OK;
@@ -675,6 +718,16 @@ int gs_resolve_rgb8(gs_scene* s, const void* d_accum, int32_t width, int32_t hei
 	GS_CUDA(cudaStreamSynchronize(st));
 	return GS_OK;
 }
+
+#ifdef GS_DIVERGENCE_STATS
+// diagnostic builds only: the raw device counters, read and reset
+int gs_debug_counters(gs_scene* s, unsigned long long* out) {
+	GS_CUDA(cudaDeviceSynchronize());
+	GS_CUDA(cudaMemcpy(out, s->stats.p, kStatSlots * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+	GS_CUDA(cudaMemset(s->stats.p + 4, 0, (kStatSlots - 4) * sizeof(unsigned long long)));
+	return GS_OK;
+}
+#endif
 
 int gs_stats_read(gs_scene* s, gs_stats* stats) {
 	int rc = check_device(s);

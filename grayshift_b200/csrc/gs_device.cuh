@@ -144,7 +144,8 @@ struct Ray {
 struct Hit {
 	double t;
 	uint32_t ref;  // kind<<30 | index into spheres/quads; 0xffffffff = miss
-	float u, v;    // quad barycentrics (alpha, beta) / triangle (u, v) for the textures; spheres compute uv on demand
+	float u, v;    // triangle (u, v) for the textures (only kernels built for triangles touch them); spheres and quads
+	               // compute their texture coordinates on demand
 };
 constexpr uint32_t kNoHit = 0xffffffffu;
 
@@ -295,7 +296,6 @@ struct RayConsts {  // per-ray values derived from the Ray; recomputed whenever 
 	float idx, idy, idz;     // 1 / direction
 	float oix, oiy, oiz;     // origin * (1 / direction): slab distance = fma(plane, id, -oi)
 	float tmax32;            // fp32 upper bound of the current closest t, for box culling
-	double a, inv_a;         // |d|^2, Vec3::length_squared (sphere.rs:71), and its reciprocal
 };
 
 __device__ __forceinline__ float tmax_to_f32(double t) { return t >= 3.0e38 ? 3.4028235e38f : __double2float_ru(t); }
@@ -304,8 +304,6 @@ __device__ __forceinline__ RayConsts ray_consts(const Ray& r, double t_closest) 
 	RayConsts c;
 	c.idx = safe_rcp((float)r.dx); c.idy = safe_rcp((float)r.dy); c.idz = safe_rcp((float)r.dz);
 	c.oix = (float)r.ox * c.idx; c.oiy = (float)r.oy * c.idy; c.oiz = (float)r.oz * c.idz;
-	c.a = r.dx * r.dx + r.dy * r.dy + r.dz * r.dz;
-	c.inv_a = f64_rcp(c.a);
 	c.tmax32 = tmax_to_f32(t_closest);
 	return c;
 }
@@ -397,8 +395,11 @@ __device__ __forceinline__ void leaf_intersect(const DeviceScene& sc, const Ray&
 			if (hit_triangle(tr, r, tmin, best.t, t, u, v)) { best.t = t; best.ref = ref; best.u = (float)u; best.v = (float)v; }
 		} else if (kind == 0u) {
 			const DSphere s = load_sphere(sc.spheres, index);
+			// |d|^2 (Vec3::length_squared, sphere.rs:71) and its reciprocal are recomputed per test: eleven f64
+			// instructions, against four registers held through the whole traversal of a register-bound kernel
+			const double a = r.dx * r.dx + r.dy * r.dy + r.dz * r.dz, inv_a = f64_rcp(a);
 			double t;
-			if (hit_sphere(s, sc.sph_path, index, r, rc.a, rc.inv_a, tmin, best.t, t)) { best.t = t; best.ref = ref; }
+			if (hit_sphere(s, sc.sph_path, index, r, a, inv_a, tmin, best.t, t)) { best.t = t; best.ref = ref; }
 		} else {
 			const DQuad q = load_quad(sc.quads, index);
 			double t, al, be;
@@ -407,7 +408,9 @@ __device__ __forceinline__ void leaf_intersect(const DeviceScene& sc, const Ray&
 				bool accept = true;
 				if (t == best.t && best.ref != kNoHit && (best.ref >> kRefKindShift) == 1u)
 					accept = __ldg(sc.quad_order + index) > __ldg(sc.quad_order + (best.ref & kRefIndexMask));
-				if (accept) { best.t = t; best.ref = ref; best.u = (float)al; best.v = (float)be; }
+				// (alpha, beta) are the quad's texture coordinates (quad.rs:101-102); the render kernels recompute them from
+				// the hit point when an image texture asks for them instead of carrying two registers through the traversal
+				if (accept) { best.t = t; best.ref = ref; }
 			}
 		}
 	}

@@ -120,9 +120,10 @@ struct Surface {
 	double px, py, pz;  // hit position (f64: it is the next ray's origin)
 	f3 n;               // shading normal, flipped against the ray (hittable.rs:35-36)
 	f3 n_out;           // outward (unflipped) normal; spheres derive (u,v) from it
-	float u, v;
+	float u, v;         // triangles only; see quad_index
 	bool front, is_sphere;
 	int material;
+	int quad_index;     // >= 0: a quad, whose (u, v) = (alpha, beta) are computed from the hit point when a texture needs them
 };
 
 __device__ __forceinline__ f3 texture_value(const DeviceScene& sc, const uint8_t* __restrict__ perm, int tex, const Surface& s, uint32_t& tex_fetches) {
@@ -143,6 +144,12 @@ __device__ __forceinline__ f3 texture_value(const DeviceScene& sc, const uint8_t
 		}
 		if (head.x == 2) {  // ImageTexture: nearest texel, v flipped, /255 (texture.rs:84-94); Q13 clamps the index
 			float u = s.u, v = s.v;
+			if (s.quad_index >= 0) {  // alpha = w.(planar x v), beta = w.(u x planar), quad.rs:88-89, as P.A - qa and P.B - qb
+				const double2* qp = reinterpret_cast<const double2*>(sc.quads + s.quad_index);
+				const double2 a01 = __ldg(qp + 2), a23 = __ldg(qp + 3), b01 = __ldg(qp + 4), b23 = __ldg(qp + 5);
+				u = (float)((s.px * a01.x + s.py * a01.y + s.pz * a23.x) - a23.y);
+				v = (float)((s.px * b01.x + s.py * b01.y + s.pz * b23.x) - b23.y);
+			}
 			if (s.is_sphere) {  // sphere_uv, sphere.rs:55-60
 				float theta = acosf(fminf(fmaxf(-s.n_out.y, -1.0f), 1.0f));
 				float phi = atan2f(-s.n_out.z, s.n_out.x) + kPi;
@@ -371,7 +378,7 @@ __device__ __forceinline__ bool segment_shade(const DeviceScene& sc, const DCame
 			// normalises it in its ONB; Metal and Dielectric reflect about it as it is)
 			const DTriangle tr = load_triangle(sc.tris, index);
 			n_out = mk3((float)(tr.e2y * tr.e1z - tr.e2z * tr.e1y), (float)(tr.e2z * tr.e1x - tr.e2x * tr.e1z), (float)(tr.e2x * tr.e1y - tr.e2y * tr.e1x));
-			s.is_sphere = false; s.u = h.u; s.v = h.v;
+			s.is_sphere = false; s.u = h.u; s.v = h.v; s.quad_index = -1;
 			s.material = __ldg(sc.tri_aux + index).x;
 		} else if ((h.ref >> kRefKindShift) == 0u) {
 			DSphere sp = load_sphere(sc.spheres, index);
@@ -379,19 +386,19 @@ __device__ __forceinline__ bool segment_shade(const DeviceScene& sc, const DCame
 			if (rad < 0.0) { double4 p = sc.sph_path[index]; cx += ray.time * p.x; cy += ray.time * p.y; cz += ray.time * p.z; rad = -rad; }
 			const float inv_r = 1.0f / (float)rad;  // outward_normal = (p - c) / r (sphere.rs:91), difference in f64, quotient in f32
 			n_out = mk3((float)(s.px - cx) * inv_r, (float)(s.py - cy) * inv_r, (float)(s.pz - cz) * inv_r);
-			s.is_sphere = true; s.u = 0.f; s.v = 0.f;
+			s.is_sphere = true; s.u = 0.f; s.v = 0.f; s.quad_index = -1;
 			s.material = __ldg(sc.sph_aux + index).x;
 		} else {
 			const double2* qp = reinterpret_cast<const double2*>(sc.quads + index);
 			double2 n01 = __ldg(qp), n23 = __ldg(qp + 1);
 			n_out = mk3((float)n01.x, (float)n01.y, (float)n23.x);
-			s.is_sphere = false; s.u = h.u; s.v = h.v;
+			s.is_sphere = false; s.u = 0.f; s.v = 0.f; s.quad_index = (int)index;
 			s.material = __ldg(sc.quad_aux + index).x;
 		}
 	} else {  // medium event: normal (1,0,0), u = v = 0, phase function as the material (volume.rs:54-62, Q10)
 		s.px = ray.ox + ray.dx * tmax; s.py = ray.oy + ray.dy * tmax; s.pz = ray.oz + ray.dz * tmax;
 		n_out = mk3(1.f, 0.f, 0.f);
-		s.is_sphere = false; s.u = 0.f; s.v = 0.f;
+		s.is_sphere = false; s.u = 0.f; s.v = 0.f; s.quad_index = -1;
 		s.material = sc.media[medium_hit].phase_mat;
 	}
 	s.front = dot(d_in, n_out) < 0.0f;  // HitRecord::new, hittable.rs:35-36

@@ -25,21 +25,25 @@ namespace gs {
 enum LaneState : int { kDead = 0, kTraverse = 1, kShade = 2, kSetup = 3 };
 // Tuning knobs (overridable with -D for the A/B sweeps of scripts/gpu_sweep.sh; defaults = the measured best).
 #ifndef GS_MIN_SHADE
-#define GS_MIN_SHADE 32   // leave phase B once this many lanes wait for shading (32 = run every ray to completion)
+#define GS_MIN_SHADE 24   // leave phase B once this many lanes have finished their ray (32 = classic while-while, every ray to completion)
 #endif
 #ifndef GS_MIN_BLOCKS
-#define GS_MIN_BLOCKS 6   // __launch_bounds__ min CTAs per SM (register cap = 65536 / (128 * GS_MIN_BLOCKS)).  The kernel is latency-
-                          // bound: 6 (80 registers, 24 warps/SM, ~240 B of spills that ptxas places in the shading code, none in
-                          // the traversal loop) measured +8 % C4 / +11 % C1 / +12 % C3 over 4 (114 registers, no spills); 7 and 8
-                          // spill more than they gain.  Parking the cold path state in shared memory instead (12 KB per CTA) was
-                          // slower than the spills: the L1 capacity it takes away costs more.
+#define GS_MIN_BLOCKS 5   // __launch_bounds__ min CTAs per SM (register cap = 65536 / (128 * GS_MIN_BLOCKS)).  The kernel is latency-
+                          // bound, so occupancy pays until spills eat the L1: 5 = 96 registers, 20 warps/SM, no spills -> best on
+                          // C4 (1518 M paths/s; its 0.5 MB scene is the one that does not fit the L1); 6 = 80 registers with 256 B
+                          // of spills in the shading code -> 1446 on C4 but +5 % on C1 and +7 % on C3 (small scenes); 4 = 110
+                          // registers -> 1403.  profiles/r01_v5_variant_sweeps.log
 #endif
 #ifndef GS_TOP_SMEM
 #define GS_TOP_SMEM 0     // nodes of the top BVH levels (breadth-first prefix) staged in shared memory per CTA; 0 = off
 #endif
 constexpr int kTopNodes = GS_TOP_SMEM;
 static_assert(kTopNodes <= kNodePad, "gs_scene_create pads the node array to kNodePad entries");
+#ifndef GS_BAIL
+#define GS_BAIL 6         // resumable traversal: the node loop of a round ends once no more than this many lanes still descend
+#endif
 constexpr int kMinShade = GS_MIN_SHADE;
+constexpr int kBail = GS_BAIL;
 
 // kF: bit 0 = count BVH node visits, bit 1 = the scene holds triangles
 template <int kF>
@@ -52,37 +56,48 @@ __global__ void __launch_bounds__(kBlock, GS_MIN_BLOCKS) render_fixed_kernel(con
 	const unsigned lane = threadIdx.x & 31u;
 	const unsigned lt_mask = (1u << lane) - 1u;
 	PathCounters pc = {0u, 0u, 0u};
-	unsigned paths = 0;
 	PathState st;
 	int state = kDead;
 	TravState tv;
 	tv.node = kStackSentinel; tv.sp = 0;
-	double seg_tmax = 0.0;
 	int seg_medium = -1;
 	int stack[kMaxStack];
-	float ar = 0.f, ag = 0.f, ab = 0.f, an = 0.f;
-	uint32_t cur_pixel = 0xffffffffu;
-	// the warp's current chunk of work items [next, end): warp-uniform, kept in shared memory rather than in four
-	// registers of every lane (the kernel is register-bound: 16 warps per SM at 114 registers)
-	__shared__ unsigned long long s_chunk[kBlock / 32][2];
+	// The kernel is register-bound (80 registers = 24 warps per SM), so what is touched once per PATH lives in shared
+	// memory instead of in registers held through every traversal: the lane's running sum for its current pixel
+	// (float4 + pixel id, [field][thread]: conflict-free) and the warp's current chunk of work items [next, end) with
+	// its "no more chunks" flag (warp-uniform).  2.6 KB per CTA; parking the whole path state the same way (12 KB) was
+	// measured slower -- the L1 capacity it takes away costs more than the spills it saves.
+	__shared__ float s_sum[4][kBlock];
+	__shared__ uint32_t s_pix[kBlock];
+	__shared__ unsigned long long s_chunk[kBlock / 32][3];
 	unsigned long long* const chunk = s_chunk[threadIdx.x >> 5];
-	if (lane == 0) { chunk[0] = 0ull; chunk[1] = 0ull; }
+	s_pix[threadIdx.x] = 0xffffffffu;
+	if (lane == 0) { chunk[0] = 0ull; chunk[1] = 0ull; chunk[2] = 0ull; }
 	__syncwarp();
-	bool exhausted = false;
 
+	auto flush_pixel = [&]() {
+		const unsigned t = threadIdx.x;
+		if (s_pix[t] != 0xffffffffu) red_add_v4(P.accum + s_pix[t], s_sum[0][t], s_sum[1][t], s_sum[2][t], s_sum[3][t]);
+	};
 	auto finish_path = [&]() {  // pixel_color += sample_color, camera.rs:141
-		if (st.pixel() != cur_pixel) {
-			if (cur_pixel != 0xffffffffu) red_add_v4(P.accum + cur_pixel, ar, ag, ab, an);
-			cur_pixel = st.pixel(); ar = ag = ab = an = 0.f;
-		}
-		ar += st.L.x; ag += st.L.y; ab += st.L.z; an += 1.f;
+		const unsigned t = threadIdx.x;
+		float ar = st.L.x, ag = st.L.y, ab = st.L.z, an = 1.f;
+		if (st.pixel() != s_pix[t]) {
+			flush_pixel();
+			s_pix[t] = st.pixel();
+		} else { ar += s_sum[0][t]; ag += s_sum[1][t]; ab += s_sum[2][t]; an += s_sum[3][t]; }
+		s_sum[0][t] = ar; s_sum[1][t] = ag; s_sum[2][t] = ab; s_sum[3][t] = an;
 		state = kDead;
 	};
 
 	for (;;) {
 		// ---- phase A1: shade the lanes whose traversal finished --------------------------------------
 		if (state == kShade) {
-			if (segment_shade<(kF & 2) != 0>(P.sc, P.cam, s_perm, st, pc, tv.best, seg_tmax, seg_medium)) finish_path();
+			// the RNG key is a kernel parameter: re-reading it here ends the live range of two registers before phase B
+			st.rng.k0 = (uint32_t)P.seed; st.rng.k1 = (uint32_t)(P.seed >> 32);
+			// (tv.best.t doubles as the medium's event distance: it starts as the medium candidate and only a closer
+			// surface hit lowers it)
+			if (segment_shade<(kF & 2) != 0>(P.sc, P.cam, s_perm, st, pc, tv.best, tv.best.t, seg_medium)) finish_path();
 			else state = kSetup;
 			if (!(kF & 1)) pc.tex_fetches = 0u;  // texel fetches are a statistic of the counting variant only (one register less here)
 		}
@@ -90,8 +105,9 @@ __global__ void __launch_bounds__(kBlock, GS_MIN_BLOCKS) render_fixed_kernel(con
 		const unsigned dead = __ballot_sync(kFull, state == kDead);
 		if (dead) {
 			unsigned long long warp_next = chunk[0], warp_end = chunk[1];
+			bool exhausted = chunk[2] != 0ull;
 			if (!(exhausted && warp_next >= warp_end)) {
-				if (warp_next >= warp_end && !exhausted) {
+				if (warp_next >= warp_end) {
 					unsigned long long base = 0;
 					if (lane == 0) base = atomicAdd(P.work_counter, (unsigned long long)P.chunk);
 					base = __shfl_sync(kFull, base, 0);
@@ -107,18 +123,18 @@ __global__ void __launch_bounds__(kBlock, GS_MIN_BLOCKS) render_fixed_kernel(con
 						const uint32_t sample = (uint32_t)(item % P.sample_count) + P.sample_begin;
 						path_begin(st, P.cam, P.seed, pixel, sample);
 						state = kSetup;
-						++paths;
 					}
 				}
 				const unsigned long long need = (unsigned long long)__popc(dead);
 				warp_next += need < avail ? need : avail;
 				__syncwarp();
-				if (lane == 0) { chunk[0] = warp_next; chunk[1] = warp_end; }
+				if (lane == 0) { chunk[0] = warp_next; chunk[1] = warp_end; chunk[2] = exhausted ? 1ull : 0ull; }
 				__syncwarp();
 			}
 		}
 		// ---- phase A3: depth test, media, traversal set-up for every fresh ray ----------------------------
 		if (state == kSetup) {
+			double seg_tmax;
 			if (segment_begin(P.sc, P.cam, st, pc, seg_tmax, seg_medium)) {
 				trav_init(P.sc, tv, stack, seg_tmax);
 				state = kTraverse;
@@ -126,34 +142,86 @@ __global__ void __launch_bounds__(kBlock, GS_MIN_BLOCKS) render_fixed_kernel(con
 		}
 		const unsigned trav0 = __ballot_sync(kFull, state == kTraverse);
 		if (trav0 == 0u) {
-			if (exhausted && chunk[0] >= chunk[1] && __ballot_sync(kFull, state != kDead) == 0u) break;
+			if (chunk[2] != 0ull && chunk[0] >= chunk[1] && __ballot_sync(kFull, state != kDead) == 0u) break;
 			continue;
 		}
 		// ---- phase B: traverse until enough lanes have finished their ray ---------------------------------
 		RayConsts rc;
 		if (state == kTraverse) rc = ray_consts(st.ray, tv.best.t);
-#if GS_MIN_SHADE >= 32
+#ifdef GS_DIVERGENCE_STATS
+		// Diagnostic build (scripts/build_variants.sh ... -DGS_DIVERGENCE_STATS): the same while-while policy written
+		// as a converged loop so that every warp-level iteration can record what the 32 lanes are doing.  Totals go to
+		// stats[4..]: node iterations, lanes stepping / waiting on a leaf / finished or without a ray in them;
+		// leaf rounds, lanes intersecting spheres / quads in them, lanes finished.
+		{
+			unsigned long long c_iter = 0, c_step = 0, c_wait = 0, c_done = 0, l_round = 0, l_sph = 0, l_quad = 0, l_done = 0;
+			const bool trav = state == kTraverse;
+			for (;;) {
+				for (;;) {
+					const bool step = trav && tv.node >= 0;
+					const unsigned ms = __ballot_sync(kFull, step);
+					if (ms == 0u) break;
+					const unsigned mw = __ballot_sync(kFull, trav && tv.node < 0 && tv.node != kStackSentinel);
+					c_iter += 1; c_step += __popc(ms); c_wait += __popc(mw); c_done += 32 - __popc(ms) - __popc(mw);
+					if (step) node_step<(kF & 1) != 0, kTopNodes>(P.sc, rc, tv, stack, &pc.node_visits, s_top);
+				}
+				const bool leaf = trav && tv.node < 0 && tv.node != kStackSentinel;
+				const unsigned ml = __ballot_sync(kFull, leaf);
+				if (ml == 0u) break;
+				const unsigned kind = leaf ? (((uint32_t)(-1 - tv.node) >> 4) >> 25) : 9u;
+				const unsigned m0 = __ballot_sync(kFull, kind == 0u);
+				l_round += 1; l_sph += __popc(m0); l_quad += __popc(ml) - __popc(m0); l_done += 32 - __popc(ml);
+				if (leaf) leaf_step<(kF & 2) != 0>(P.sc, st.ray, rc, 0.001, tv, stack);
+			}
+			if (trav) state = kShade;
+			if (lane == 0) {
+				atomicAdd(P.stats + 4, c_iter); atomicAdd(P.stats + 5, c_step); atomicAdd(P.stats + 6, c_wait); atomicAdd(P.stats + 7, c_done);
+				atomicAdd(P.stats + 8, l_round); atomicAdd(P.stats + 9, l_sph); atomicAdd(P.stats + 10, l_quad); atomicAdd(P.stats + 11, l_done);
+				atomicAdd(P.stats + 12, 1ull); atomicAdd(P.stats + 13, (unsigned long long)__popc(trav0));
+			}
+		}
+#elif GS_MIN_SHADE >= 32
 		// Every lane runs its ray to completion (classic while-while); measured best on B200.
 		if (state == kTraverse) {
 			while (tv.node != kStackSentinel) trav_round<kF, kTopNodes>(P.sc, st.ray, rc, 0.001, tv, stack, &pc.node_visits, s_top);
 			state = kShade;
 		}
 #else
-		// Resumable while-while rounds: leave as soon as kMinShade lanes have finished their ray.
+		// Converged, resumable traversal.  Measured lane occupancy of the classic loop on C4 (GS_DIVERGENCE_STATS build,
+		// profiles/r01_v5_divergence.log): per node-loop iteration 8.2 lanes step, 4.8 wait on a leaf for the others and
+		// 19.0 have FINISHED their ray -- ray lengths are close to exponential (mean 11 node steps, the longest of 32 ~44),
+		// so the warp mostly waits for its longest ray.  Here all 32 lanes stay in one loop, two ballots per iteration
+		// tell how many lanes step / wait on a leaf / are finished, and the warp
+		//   * leaves for phase A as soon as kMinShade lanes are finished (the others keep node, sp, best, stack and
+		//     resume in the next phase B),
+		//   * runs the leaf code once kLeafT lanes wait on a leaf (or nobody can step).
+		// (Lanes without a ray at entry -- only at the very end of the image -- do not count as finished: with fewer than
+		// kMinShade rays in the warp, all of them run to completion.)
+		const int n_trav0 = __popc(trav0), exit_at = n_trav0 < kMinShade ? n_trav0 : kMinShade;
+		const bool trav = state == kTraverse;
 		for (;;) {
-			const bool trav = state == kTraverse;
-			const unsigned m_trav = __ballot_sync(kFull, trav);
-			const unsigned m_shade = __ballot_sync(kFull, state == kShade);
-			if (m_trav == 0u || __popc(m_shade) >= kMinShade) break;
-			if (trav) {
-				trav_round<kF, kTopNodes>(P.sc, st.ray, rc, 0.001, tv, stack, &pc.node_visits, s_top);
-				if (tv.node == kStackSentinel) state = kShade;
+			// node phase: the classic tight per-lane loop, except that the lanes still descending give up once no more than
+			// kBail of them are left (__activemask() = the lanes still inside this loop; the others wait at its exit), so
+			// a round lasts as long as the kBail-th slowest lane needs, not the slowest.  The stragglers sit out the leaf
+			// phase and carry on in the next round.  (A fully converged loop with two ballots per node step was measured
+			// 10-15 % slower than the classic loop: 12 more instructions per step, and ptxas spilled the ray constants.)
+			if (trav && tv.node >= 0) {
+				do node_step<(kF & 1) != 0, kTopNodes>(P.sc, rc, tv, stack, &pc.node_visits, s_top);
+				while (tv.node >= 0 && __popc(__activemask()) > kBail);
 			}
+			__syncwarp();
+			const bool leaf = trav && tv.node < 0 && tv.node != kStackSentinel;
+			const unsigned m_live = __ballot_sync(kFull, leaf || (trav && tv.node >= 0));
+			if (n_trav0 - __popc(m_live) >= exit_at) break;
+			if (leaf) leaf_step<(kF & 2) != 0>(P.sc, st.ray, rc, 0.001, tv, stack);
 		}
+		if (state == kTraverse && tv.node == kStackSentinel) state = kShade;
 #endif
 	}
-	if (cur_pixel != 0xffffffffu) red_add_v4(P.accum + cur_pixel, ar, ag, ab, an);
-	flush_stats(P.stats, pc, paths);
+	flush_pixel();
+	// every work item starts exactly one path: no per-lane counter for them
+	flush_stats(P.stats, pc, 0u);
+	if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(P.stats + 1, P.total_items);
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
