@@ -101,7 +101,8 @@ struct DCamera {
 // rounds stay inline and rolled up: 10 iterations of 8 instructions instead of 25 inlined copies of 80.)
 __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
 #ifndef GS_PHILOX_UNROLL
-#define GS_PHILOX_UNROLL 1  // tuning knob: 1 = rolled loop (small code), 10 = fully unrolled
+#define GS_PHILOX_UNROLL 2  // tuning knob: 1 = rolled loop (11 instructions per round), 2 = two rounds per iteration (7.5 per round; measured +1 % C4,
+                            // +5 % C1), 5 / 10 = more unrolling: faster on C1/C3 but -10...-15 % on C4, whose many code paths overflow the I-cache
 #endif
 #define GS_STR_(x) #x
 #define GS_PRAGMA_UNROLL_(n) _Pragma(GS_STR_(unroll n))

@@ -23,12 +23,10 @@ __device__ __forceinline__ void load_perm(uint8_t* s_perm, const uint8_t* g_perm
 
 // Per-thread counters -> device totals: warp shuffle reduction, one atomic per warp and counter.
 __device__ __forceinline__ void flush_stats(unsigned long long* stats, const PathCounters& pc, unsigned paths) {
-	unsigned r = pc.rays, t = pc.tex_fetches, n = pc.node_visits, p = paths;
-#pragma unroll
-	for (int o = 16; o > 0; o >>= 1) {
-		r += __shfl_xor_sync(kFull, r, o); t += __shfl_xor_sync(kFull, t, o);
-		n += __shfl_xor_sync(kFull, n, o); p += __shfl_xor_sync(kFull, p, o);
-	}
+	// one REDUX per counter (a shuffle tree costs five shuffles each plus their divergence fall-backs: 400 instructions
+	// of a kernel that is sensitive to its code size)
+	const unsigned r = __reduce_add_sync(kFull, pc.rays), t = __reduce_add_sync(kFull, pc.tex_fetches);
+	const unsigned n = __reduce_add_sync(kFull, pc.node_visits), p = __reduce_add_sync(kFull, paths);
 	if ((threadIdx.x & 31) == 0) {
 		if (r) atomicAdd(stats + 0, (unsigned long long)r);
 		if (p) atomicAdd(stats + 1, (unsigned long long)p);

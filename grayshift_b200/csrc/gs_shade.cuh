@@ -191,9 +191,16 @@ __device__ __forceinline__ bool shade(const DeviceScene& sc, const uint8_t* __re
 	const int4 m0 = __ldg(reinterpret_cast<const int4*>(mp));        // kind, tex, albedo.r, albedo.g
 	const float4 m1 = __ldg(reinterpret_cast<const float4*>(mp) + 1);  // albedo.b, param
 	emit = mk3(0.f, 0.f, 0.f);
-	switch (m0.x) {
+	// One copy of the texture evaluation (the Perlin turbulence is ~500 instructions) and of the unit-vector rejection loop
+	// for all materials that use them: the megakernel is instruction-cache sensitive.  Textures draw no random numbers,
+	// so the draw order of every material is unchanged.
+	const int kind = m0.x;
+	f3 tex = mk3(0.f, 0.f, 0.f), ruv = mk3(0.f, 0.f, 0.f);
+	if (kind == 0 || kind >= 3) tex = texture_value(sc, perm, m0.y, s, tex_fetches);
+	if (kind == 1 || kind >= 4) ruv = random_unit_vector(rng);
+	switch (kind) {
 		case 0: {  // Lambertian
-			atten = texture_value(sc, perm, m0.y, s, tex_fetches);
+			atten = tex;
 			// OrthonormalBasis::new, ONB.rs:10-23
 			f3 w = unit(s.n);
 			f3 a = fabsf(w.x) > 0.9f ? mk3(0.f, 1.f, 0.f) : mk3(1.f, 0.f, 0.f);
@@ -205,8 +212,7 @@ __device__ __forceinline__ bool shade(const DeviceScene& sc, const uint8_t* __re
 		}
 		case 1: {  // Metal: unit(reflect) + fuzz * random_unit_vector, drawn even when fuzz == 0 (Q7)
 			f3 refl = d_in - s.n * (2.0f * dot(d_in, s.n));
-			f3 rv = random_unit_vector(rng);
-			d_out = unit(refl) + rv * m1.y;
+			d_out = unit(refl) + ruv * m1.y;
 			atten = mk3(__int_as_float(m0.z), __int_as_float(m0.w), m1.x);
 			return dot(d_out, s.n) > 0.0f;
 		}
@@ -233,12 +239,12 @@ __device__ __forceinline__ bool shade(const DeviceScene& sc, const uint8_t* __re
 			return true;
 		}
 		case 3: {  // DiffuseLight: two-sided, never scatters (Q8)
-			emit = texture_value(sc, perm, m0.y, s, tex_fetches);
+			emit = tex;
 			return false;
 		}
 		default: {  // Isotropic
-			atten = texture_value(sc, perm, m0.y, s, tex_fetches);
-			d_out = random_unit_vector(rng);
+			atten = tex;
+			d_out = ruv;
 			return true;
 		}
 	}
@@ -295,8 +301,14 @@ __device__ __forceinline__ bool medium_event(const DeviceScene& sc, const DMediu
 		if (!(t1 > -kMax && t1 < kMax)) return false;
 		if (!(t1 + 0.0001 < t2 && t2 < kMax)) return false;
 	} else {
-		if (!boundary_closest(sc, m, r, a, inv_a, -kMax, kMax, t1)) return false;  // Interval::UNIVERSE
-		if (!boundary_closest(sc, m, r, a, inv_a, t1 + 0.0001, kMax, t2)) return false;
+		// boundary.hit(UNIVERSE), then boundary.hit([t1 + 1e-4, MAX)), volume.rs:33-37 (one copy of the code, two passes)
+		t1 = -kMax;
+#pragma unroll 1
+		for (int pass = 0; pass < 2; ++pass) {
+			double t;
+			if (!boundary_closest(sc, m, r, a, inv_a, pass == 0 ? -kMax : t1 + 0.0001, kMax, t)) return false;
+			if (pass == 0) t1 = t; else t2 = t;
+		}
 	}
 	if (t1 < tmin) t1 = tmin;
 	if (t2 > tmax) t2 = tmax;
