@@ -2,6 +2,8 @@
 // the host's flat scene description for the GPU, upload, kernel launches, resolve.  Host code only;
 // the kernels live in render_kernels.cu and trace_closest.cu.  There is no CPU compute path here:
 // without a CUDA device every compute entry fails with GS_ERR_NO_DEVICE.
+#include <algorithm>
+#include <array>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -87,6 +89,7 @@ struct gs_scene {
 	double max_abs_coord = 0.0;
 
 	DevBuf<DNode> nodes;
+	DevBuf<DNode4> nodes4;  // GS_WIDE builds
 	DevBuf<uint32_t> refs;
 	DevBuf<DSphere> spheres;
 	DevBuf<double4> sph_path;
@@ -107,6 +110,11 @@ struct gs_scene {
 	std::vector<gs_image> h_images;  // sizes/formats for validation of camera.hdri_image
 	DevBuf<uint8_t> perm;
 	DeviceScene ds{};
+
+	// adaptive sampler: the two lists of pixels still sampling, their lengths, per-pixel (sum lum, sum lum^2)
+	DevBuf<uint32_t> px_list[2];
+	DevBuf<unsigned> px_count;
+	DevBuf<double2> lum;
 
 	// render scratch
 	DevBuf<float4> accum;
@@ -138,7 +146,8 @@ struct gs_scene {
 		pool_org.release(); pool_dir.release(); pool_thr.release(); pool_rad.release(); pool_ids.release(); pool_hit.release();
 		free_list.release(); wave_ctr.release();
 		if (h_wave_ctr) cudaFreeHost(h_wave_ctr);
-		nodes.release(); refs.release(); spheres.release(); sph_path.release(); sph_aux.release(); quads.release(); quad_aux.release();
+		px_list[0].release(); px_list[1].release(); px_count.release(); lum.release();
+		nodes.release(); nodes4.release(); refs.release(); spheres.release(); sph_path.release(); sph_aux.release(); quads.release(); quad_aux.release();
 		quad_order.release(); tris.release(); tri_aux.release(); bnd_spheres.release(); bnd_sph_path.release(); bnd_quads.release(); media.release(); materials.release();
 		textures.release(); images.release(); perm.release(); accum.release(); out_rgb.release(); out_counts.release(); counters.release();
 		stats.release();
@@ -261,8 +270,112 @@ int validate(const gs_scene_desc* d) {
 
 // (Re)build the device node array from the ABI nodes with boxes padded for fp32 traversal of rays
 // whose origins lie within `origin_limit` of the world origin.
+#if GS_WIDE
+// The wide tree: every binary node that stays internal takes its two children and, twice, replaces the internal child
+// with the largest surface area by that child's own two children (up to four).  Child boxes are padded for the fp32
+// slab test exactly like the binary nodes (plus the rounding of the quantised decode), then stored as 8-bit offsets
+// on a power-of-two grid from the node's lower corner: lower planes rounded down, upper planes up -- conservative.
+int build_nodes_wide(gs_scene* s, double origin_limit) {
+	const float lim = (float)origin_limit;
+	// 8 ulp as for the binary nodes + 4 for the two extra roundings of t = q * (step / d) + (corner - o) / d
+	const double pad = 12.0 * (double)(std::nextafterf(lim, INFINITY) - lim);
+	const std::vector<gs_bvh_node>& N = s->h_nodes;
+	auto internal = [&](int a) { return N[a].ref_count == 0; };
+	auto area = [&](int a) {
+		const double dx = N[a].bounds_max[0] - N[a].bounds_min[0], dy = N[a].bounds_max[1] - N[a].bounds_min[1], dz = N[a].bounds_max[2] - N[a].bounds_min[2];
+		return dx * dy + dy * dz + dz * dx;
+	};
+	std::vector<DNode4> out;
+	if (!N.empty() && internal(0)) {
+		std::vector<int> queue{0};          // binary nodes that become wide nodes, breadth-first = device order
+		std::vector<std::array<int, 4>> kids_of;
+		std::vector<int> n_kids_of;
+		std::vector<int> wide_index(N.size(), -1);
+		wide_index[0] = 0;
+		for (size_t h = 0; h < queue.size(); ++h) {
+			const int a = queue[h];
+			std::array<int, 4> kids{N[a].left, N[a].right, -1, -1};
+			int n = 2;
+			while (n < 4) {
+				int best = -1;
+				for (int k = 0; k < n; ++k)
+					if (internal(kids[k]) && (best < 0 || area(kids[k]) > area(kids[best]))) best = k;
+				if (best < 0) break;
+				const int c = kids[best];
+				kids[best] = N[c].left;
+				kids[n++] = N[c].right;
+			}
+			for (int k = 0; k < n; ++k)
+				if (internal(kids[k])) { wide_index[kids[k]] = (int)queue.size(); queue.push_back(kids[k]); }
+			kids_of.push_back(kids);
+			n_kids_of.push_back(n);
+		}
+		// worst-case stack use: (children - 1) siblings pushed at every level of the deepest chain
+		std::vector<int> need(queue.size(), 0);
+		for (size_t h = queue.size(); h-- > 0;) {
+			int deepest = 0;
+			for (int k = 0; k < n_kids_of[h]; ++k)
+				if (internal(kids_of[h][k])) deepest = std::max(deepest, need[wide_index[kids_of[h][k]]]);
+			need[h] = n_kids_of[h] - 1 + deepest;
+		}
+		if (need[0] + 2 > kMaxStack) return fail(GS_ERR_UNSUPPORTED, "wide BVH needs a deeper traversal stack than the kernels have");
+		out.resize(queue.size());
+		for (size_t h = 0; h < queue.size(); ++h) {
+			float lo[4][3], hi[4][3];
+			float corner[3] = {INFINITY, INFINITY, INFINITY}, top[3] = {-INFINITY, -INFINITY, -INFINITY};
+			const int n = n_kids_of[h];
+			for (int k = 0; k < n; ++k) {
+				const gs_bvh_node& c = N[kids_of[h][k]];
+				for (int a = 0; a < 3; ++a) {
+					lo[k][a] = float_down(c.bounds_min[a] - pad); hi[k][a] = float_up(c.bounds_max[a] + pad);
+					corner[a] = std::fmin(corner[a], lo[k][a]); top[a] = std::fmax(top[a], hi[k][a]);
+				}
+			}
+			DNode4 d;
+			std::memset(&d, 0, sizeof d);
+			d.ox = corner[0]; d.oy = corner[1]; d.oz = corner[2];
+			uint32_t q[6] = {0, 0, 0, 0, 0, 0};  // qlox, qhix, qloy, qhiy, qloz, qhiz
+			for (int a = 0; a < 3; ++a) {
+				const double extent = (double)top[a] - (double)corner[a];
+				int e = -100;  // grid step 2^e: the smallest power of two with 255 steps >= extent (never below 2^-100)
+				if (extent > 0.0) e = std::max(e, (int)std::ceil(std::log2(extent / 255.0)));
+				for (;;) {  // make sure every upper plane fits into 8 bits after rounding up
+					const double step = std::ldexp(1.0, e);
+					bool ok = true;
+					for (int k = 0; k < n && ok; ++k) ok = std::ceil(((double)hi[k][a] - (double)corner[a]) / step) <= 255.0;
+					if (ok) break;
+					++e;
+				}
+				if (e + 127 < 1 || e + 127 > 254) return fail(GS_ERR_UNSUPPORTED, "wide BVH: box extent out of the fp32 exponent range");
+				d.exps |= (uint32_t)(e + 127) << (8 * a);
+				const double step = std::ldexp(1.0, e);
+				for (int k = 0; k < n; ++k) {
+					const double ql = std::floor(((double)lo[k][a] - (double)corner[a]) / step), qh = std::ceil(((double)hi[k][a] - (double)corner[a]) / step);
+					q[2 * a] |= (uint32_t)std::min(255.0, std::max(0.0, ql)) << (8 * k);
+					q[2 * a + 1] |= (uint32_t)std::min(255.0, std::max(0.0, qh)) << (8 * k);
+				}
+			}
+			d.qlox = q[0]; d.qhix = q[1]; d.qloy = q[2]; d.qhiy = q[3]; d.qloz = q[4]; d.qhiz = q[5];
+			int lk[4] = {0, 0, 0, 0};
+			for (int k = 0; k < n; ++k) lk[k] = internal(kids_of[h][k]) ? wide_index[kids_of[h][k]] : s->h_leaf_code[kids_of[h][k]];
+			d.link = make_int4(lk[0], lk[1], lk[2], lk[3]);
+			out[h] = d;
+		}
+	}
+	if (out.empty()) { DNode4 d; std::memset(&d, 0, sizeof d); out.push_back(d); }  // single-leaf tree: keep the pointer valid
+	GS_CUDA(s->nodes4.upload(out));
+	s->h2d_bytes += out.size() * sizeof(DNode4);
+	s->ds.nodes4 = s->nodes4.p;
+	s->ds.nodes = nullptr;
+	return GS_OK;
+}
+#endif
+
 int build_nodes(gs_scene* s, double origin_limit) {
 	s->origin_limit = origin_limit;
+#if GS_WIDE
+	return build_nodes_wide(s, origin_limit);
+#endif
 	// fp32 error budget: origin and plane rounding (<= 1 ulp at origin_limit), subtraction, reciprocal
 	// and product (relative 2^-23 each over distances <= 2*origin_limit) -> 8 ulp(origin_limit) is safe.
 	const float lim = (float)origin_limit;
@@ -649,6 +762,7 @@ int gs_render_accumulate(gs_scene* s, const gs_camera* camera, uint64_t seed, ui
 	p.accum = static_cast<float4*>(d_accum);
 	p.work_counter = next_counter(s);
 	p.stats = s->stats.p;
+	p.pixel_list = nullptr; p.n_list = nullptr; p.lum = nullptr;  // every pixel, no luminance statistics
 	GS_CUDA(cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned long long), st));
 	GS_CUDA(launch_render_fixed(p, s->sm_count, s->count_nodes, s->has_triangles, st));
 	s->launches += 1;
@@ -662,27 +776,58 @@ int gs_render_adaptive_accumulate(gs_scene* s, const gs_camera* camera, const gs
 	if (!d_accum || !settings) return fail(GS_ERR_INVALID, "null argument");
 	if (settings->batch_size == 0) return fail(GS_ERR_INVALID, "batch_size must be > 0 (the reference would loop forever)");
 	if (pixel_stride == 0) return fail(GS_ERR_INVALID, "pixel_stride must be > 0");
-	AdaptiveParams p;
+	RenderParams p;
 	rc = convert_camera(s, camera, p.cam);
 	if (rc) return rc;
 	rc = ensure_origin_range(s, camera);
 	if (rc) return rc;
 	p.sc = s->ds;
 	cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-	p.seed = seed;
-	p.confidence_sq = settings->confidence * settings->confidence;  // camera.rs:128-129
-	p.tolerance_sq = settings->tolerance * settings->tolerance;
-	p.batch_size = settings->batch_size; p.max_samples = settings->max_samples;
 	const unsigned total = (unsigned)camera->image_width * (unsigned)camera->image_height;
-	p.pixel_begin = pixel_begin; p.pixel_stride = pixel_stride;
-	p.n_pixels = pixel_begin >= total ? 0u : (total - pixel_begin + pixel_stride - 1) / pixel_stride;
+	const unsigned n_pixels = pixel_begin >= total ? 0u : (total - pixel_begin + pixel_stride - 1) / pixel_stride;
+	if (n_pixels == 0) return GS_OK;
+	AdaptiveParams ap;
+	ap.confidence_sq = settings->confidence * settings->confidence;  // camera.rs:128-129
+	ap.tolerance_sq = settings->tolerance * settings->tolerance;
+	ap.max_samples = settings->max_samples;
+	ap.n_pixels = n_pixels;
+	ap.accum = static_cast<const float4*>(d_accum);
+	// Camera::sample's loop (camera.rs:135-165) leaves after the first batch that takes `sample_count as u32` past
+	// max_samples: at most max_samples / batch_size + 1 batches.
+	const unsigned long long rounds = (unsigned long long)settings->max_samples / settings->batch_size + 1ull;
+	GS_CUDA(s->px_list[0].alloc(n_pixels)); GS_CUDA(s->px_list[1].alloc(n_pixels));
+	GS_CUDA(s->px_count.alloc(2));
+	GS_CUDA(s->lum.alloc(total));
+	GS_CUDA(cudaMemsetAsync(s->lum.p, 0, (size_t)total * sizeof(double2), st));
+	GS_CUDA(launch_adaptive_init(s->px_list[0].p, s->px_count.p, pixel_begin, pixel_stride, n_pixels, st));
+	p.seed = seed;
+	p.sample_count = settings->batch_size;
+	p.total_items = (unsigned long long)n_pixels * settings->batch_size;  // upper bound; the kernel reads the list length
+	p.chunk = 256;
 	p.accum = static_cast<float4*>(d_accum);
-	p.work_counter = next_counter(s);
 	p.stats = s->stats.p;
-	if (p.n_pixels == 0) return GS_OK;
-	GS_CUDA(cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned long long), st));
-	GS_CUDA(launch_render_adaptive(p, s->sm_count, st));
-	s->launches += 1;
+	p.lum = s->lum.p;
+	for (unsigned long long r = 0; r < rounds; ++r) {
+		const int cur = (int)(r & 1ull), nxt = cur ^ 1;
+		if ((unsigned long long)settings->batch_size * (r + 1ull) > 0xffffffffull) return fail(GS_ERR_UNSUPPORTED, "sample index beyond 32 bits");
+		p.sample_begin = (unsigned)(r * settings->batch_size);
+		p.pixel_list = s->px_list[cur].p;
+		p.n_list = s->px_count.p + cur;
+		p.work_counter = next_counter(s);
+		GS_CUDA(cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned long long), st));
+		GS_CUDA(cudaMemsetAsync(s->px_count.p + nxt, 0, sizeof(unsigned), st));
+		GS_CUDA(launch_render_fixed(p, s->sm_count, false, s->has_triangles, st));
+		GS_CUDA(launch_adaptive_decide(ap, s->px_list[cur].p, s->px_count.p + cur, s->px_list[nxt].p, s->px_count.p + nxt, s->lum.p, st));
+		s->launches += 2;
+		// after batches 1, 2, 4, 8, ... look whether any pixel is still sampling (one 4-byte read): most renders end long
+		// before the cap, and a launch pair that finds an empty list still costs ~10 us
+		if (((r + 1ull) & r) == 0ull && r + 1 < rounds) {
+			unsigned left = 0;
+			GS_CUDA(cudaMemcpyAsync(&left, s->px_count.p + nxt, sizeof left, cudaMemcpyDeviceToHost, st));
+			GS_CUDA(cudaStreamSynchronize(st));
+			if (left == 0) break;
+		}
+	}
 	return GS_OK;
 }
 

@@ -19,6 +19,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#ifndef GS_WIDE
+#define GS_WIDE 0  // 1 = four-wide tree with quantised child boxes (DNode4) instead of the binary tree (DNode)
+#endif
+
 namespace gs {
 
 // ------------------------------------------------------------------------------------------
@@ -30,13 +34,29 @@ struct __align__(16) DNode {
 	float4 z01;  // c0.min.z, c0.max.z, c1.min.z, c1.max.z
 	int4 link;   // child0, child1 (>= 0 internal node index; < 0 leaf code), unused, unused
 };
+// Wide node (GS_WIDE builds): four children in 64 bytes.  The children's boxes are stored as 8-bit offsets on a
+// power-of-two grid anchored at the node's own lower corner (conservative: lower planes rounded down, upper planes up),
+// so a node costs as many bytes as a binary one but replaces two levels: half the dependent fetches and half the bytes
+// per ray.  Matters when the tree does not fit the L1 (config 5: 10^6 spheres, node fetches come from L2).
+struct __align__(16) DNode4 {
+	float ox, oy, oz;   // lower corner of the node's box (fp32, already padded outward)
+	uint32_t exps;      // byte a = biased fp32 exponent of the grid step of axis a (step = 2^(e - 127))
+	uint32_t qlox, qhix, qloy, qhiy;   // byte i = child i: lower / upper plane in grid steps from the corner
+	uint32_t qloz, qhiz;
+	int pad0, pad1;
+	int4 link;          // child i: > 0 node index, < 0 leaf code, 0 = no child (node 0 is the root, never a child)
+};
 // leaf code: -1 - ((first_ref << 4) | count), 1 <= count <= 15; count == 0 marks a single-primitive leaf whose
 // reference (kind << 25 | index) sits in the first_ref field itself
 __host__ __device__ inline int leaf_code(uint32_t first, uint32_t count) { return -1 - (int)((first << 4) | count); }
 // Negative (so the inner "internal node" loop stops on it) and not a valid leaf code: it would need
 // first_ref = 2^27 - 1 with count 15, which gs_scene_create rejects.
 constexpr int kStackSentinel = -2147483647 - 1;
+#if GS_WIDE
+constexpr int kMaxStack = 96;  // a wide node pushes up to three siblings
+#else
 constexpr int kMaxStack = 64;
+#endif
 constexpr int kNodePad = 512;  // the device node array holds at least this many entries (zero boxes beyond the tree), so a
                                // kernel may stage a fixed-size breadth-first prefix in shared memory without a bounds check
 
@@ -61,6 +81,7 @@ constexpr uint32_t kRefIndexMask = (1u << 30) - 1u;
 
 struct DeviceScene {
 	const DNode* nodes;
+	const DNode4* nodes4;  // GS_WIDE builds: the wide tree (then `nodes` is null)
 	const uint32_t* refs;
 	const DSphere* spheres;
 	const double4* sph_path;
@@ -354,6 +375,47 @@ __device__ __forceinline__ void node_test(const float4 xy0, const float4 xy1, co
 #endif
 }
 
+// One wide node (GS_WIDE): the four children's slabs from the quantised planes, t = q * (step / d) + (corner - o) / d
+// -- one FMA per plane after three multiplications and three FMAs per node -- with the near / far plane of each axis picked
+// by the sign of the direction (word select per node instead of a min and a max per child and axis).  The hit children
+// are sorted by entry distance with a five-exchange network; the nearest is visited next, the others are pushed
+// far-to-near.  Precondition: tv.node >= 0.
+__device__ __forceinline__ float q8(uint32_t w, int i) { return (float)((w >> (8 * i)) & 0xffu); }
+
+template <bool kCount>
+__device__ __forceinline__ void node_step4(const DeviceScene& sc, const RayConsts& rc, TravState& tv, int* stack, uint32_t* node_visits) {
+	const uint4* np = reinterpret_cast<const uint4*>(sc.nodes4 + tv.node);
+	const uint4 hd = __ldg(np), qa = __ldg(np + 1);
+	const uint2 qb = __ldg(reinterpret_cast<const uint2*>(np + 2));
+	const int4 link = __ldg(reinterpret_cast<const int4*>(np + 3));
+	if (kCount) ++(*node_visits);
+	const float ax = __uint_as_float((hd.w & 0xffu) << 23) * rc.idx, bx = fmaf(__uint_as_float(hd.x), rc.idx, -rc.oix);
+	const float ay = __uint_as_float(((hd.w >> 8) & 0xffu) << 23) * rc.idy, by = fmaf(__uint_as_float(hd.y), rc.idy, -rc.oiy);
+	const float az = __uint_as_float(((hd.w >> 16) & 0xffu) << 23) * rc.idz, bz = fmaf(__uint_as_float(hd.z), rc.idz, -rc.oiz);
+	const uint32_t nx = rc.idx < 0.0f ? qa.y : qa.x, fx = rc.idx < 0.0f ? qa.x : qa.y;  // near / far planes
+	const uint32_t ny = rc.idy < 0.0f ? qa.w : qa.z, fy = rc.idy < 0.0f ? qa.z : qa.w;
+	const uint32_t nz = rc.idz < 0.0f ? qb.y : qb.x, fz = rc.idz < 0.0f ? qb.x : qb.y;
+	const int lk[4] = {link.x, link.y, link.z, link.w};
+	float key[4];
+#pragma unroll
+	for (int i = 0; i < 4; ++i) {
+		const float en = fmaxf(fmaxf(fmaf(q8(nx, i), ax, bx), fmaf(q8(ny, i), ay, by)), fmaxf(fmaf(q8(nz, i), az, bz), 0.0f));
+		const float ex = fminf(fminf(fmaf(q8(fx, i), ax, bx), fmaf(q8(fy, i), ay, by)), fminf(fmaf(q8(fz, i), az, bz), rc.tmax32));
+		key[i] = (en <= ex && lk[i] != 0) ? en : __int_as_float(0x7f800000);  // +inf = not hit
+	}
+	int l0 = lk[0], l1 = lk[1], l2 = lk[2], l3 = lk[3];
+	float k0 = key[0], k1 = key[1], k2 = key[2], k3 = key[3];
+#define GS_CSWAP(ka, la, kb, lb) { const bool sw = kb < ka; const float tk = sw ? kb : ka; const int tl = sw ? lb : la; kb = sw ? ka : kb; lb = sw ? la : lb; ka = tk; la = tl; }
+	GS_CSWAP(k0, l0, k1, l1) GS_CSWAP(k2, l2, k3, l3) GS_CSWAP(k0, l0, k2, l2) GS_CSWAP(k1, l1, k3, l3) GS_CSWAP(k1, l1, k2, l2)
+#undef GS_CSWAP
+	const float inf = __int_as_float(0x7f800000);
+	if (k3 < inf) stack[tv.sp++] = l3;
+	if (k2 < inf) stack[tv.sp++] = l2;
+	if (k1 < inf) stack[tv.sp++] = l1;
+	if (k0 < inf) tv.node = l0;
+	else tv.node = stack[--tv.sp];
+}
+
 // One internal node: AABB::hit (AABB.rs:58-113) for both children at once, near child first, far child pushed.
 // Slab distances in fp32 as fma(plane, 1/d, -o/d) against boxes padded by 8 ulp of the origin range
 // (abi.cu build_nodes): conservative, never culls a true hit.  Precondition: tv.node >= 0.
@@ -362,6 +424,10 @@ __device__ __forceinline__ void node_test(const float4 xy0, const float4 xy1, co
 template <bool kCount, int kTop = 0>
 __device__ __forceinline__ void node_step(const DeviceScene& sc, const RayConsts& rc, TravState& tv, int* stack, uint32_t* node_visits,
                                           const float4* top = nullptr) {
+#if GS_WIDE
+	node_step4<kCount>(sc, rc, tv, stack, node_visits);
+	return;
+#endif
 	const float4* np = reinterpret_cast<const float4*>(sc.nodes + tv.node);
 	if (kTop > 0) {
 		if (tv.node < kTop) np = top + tv.node * 4;

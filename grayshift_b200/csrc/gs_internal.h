@@ -15,23 +15,24 @@ struct RenderParams {
 	float4* accum;                         // W*H (sum r, sum g, sum b, count)
 	unsigned long long* work_counter;      // dynamic work distribution
 	unsigned long long* stats;             // [0] rays, [1] paths, [2] texel fetches, [3] node visits
+	// adaptive rounds (Camera::sample's batch loop run as one fixed-count launch per batch over the pixels still sampling)
+	const uint32_t* pixel_list;            // work item i belongs to pixel_list[i / sample_count]; nullptr = every pixel
+	const unsigned* n_list;                // device-resident length of pixel_list (total_items is derived from it on the device)
+	double2* lum;                          // per pixel (sum of luminance, sum of its square), camera.rs:132-133,146-147
 };
 
-struct AdaptiveParams {
-	DeviceScene sc;
-	DCamera cam;
-	unsigned long long seed;
+struct AdaptiveParams {  // the stop test of camera.rs:150-164
 	double confidence_sq, tolerance_sq;
-	unsigned batch_size, max_samples;
-	unsigned pixel_begin, pixel_stride, n_pixels;  // this rank renders pixels pixel_begin + k*pixel_stride
-	float4* accum;
-	unsigned long long* work_counter;
-	unsigned long long* stats;
+	unsigned max_samples;
+	unsigned n_pixels;  // pixels this rank started with (upper bound of every list)
+	const float4* accum;
 };
 
 // launch wrappers (defined next to the kernels); all asynchronous on `stream`
 cudaError_t launch_render_fixed(const RenderParams& p, int sm_count, bool count_nodes, bool triangles, cudaStream_t stream);
-cudaError_t launch_render_adaptive(const AdaptiveParams& p, int sm_count, cudaStream_t stream);
+cudaError_t launch_adaptive_init(uint32_t* list, unsigned* n_list, unsigned pixel_begin, unsigned pixel_stride, unsigned n_pixels, cudaStream_t stream);
+cudaError_t launch_adaptive_decide(const AdaptiveParams& p, const uint32_t* list, const unsigned* n_in, uint32_t* next, unsigned* n_out,
+                                   const double2* lum, cudaStream_t stream);
 cudaError_t launch_resolve(const float4* accum, int n_pixels, float* out_rgb, unsigned* out_counts, cudaStream_t stream);
 cudaError_t launch_resolve_rgb8(const float4* accum, int n_pixels, unsigned char* out_rgb8, unsigned* out_counts, cudaStream_t stream);
 cudaError_t launch_camera_rays(const DCamera& cam, unsigned long long seed, unsigned sample, int pixel_begin, int pixel_end, double* rays_out,

@@ -7,8 +7,8 @@
 //   Work items are handed out in chunks through one global 64-bit atomic per warp per chunk.
 //   Each lane keeps (sum r, sum g, sum b, n) for its current pixel in registers and flushes with one
 //   128-bit vector reduction (red.global.add.v4.f32) when its pixel changes.
-// render_adaptive_kernel: the reference's adaptive sampler (camera.rs:125-171) with exact batch /
-//   stop-test semantics (Q3-Q5): one warp per pixel, a batch's samples spread over the lanes.
+// adaptive sampling (camera.rs:125-171, exact batch / stop-test semantics, Q3-Q5): one launch of the same megakernel per
+//   batch over the pixels still sampling + adaptive_decide_kernel (the stop test), see below.
 // Grids are sized to SM count x resident CTAs (persistent), never to the image.
 #include "gs_internal.h"
 #include "gs_kernel_util.cuh"
@@ -45,9 +45,12 @@ static_assert(kTopNodes <= kNodePad, "gs_scene_create pads the node array to kNo
 constexpr int kMinShade = GS_MIN_SHADE;
 constexpr int kBail = GS_BAIL;
 
-// kF: bit 0 = count BVH node visits, bit 1 = the scene holds triangles
+// kF: bit 0 = count BVH node visits, bit 1 = the scene holds triangles, bit 2 = one batch of the adaptive sampler (work items
+// come from a device-resident list of the pixels still sampling, and the luminance sums of camera.rs:146-147 are kept)
 template <int kF>
 __global__ void __launch_bounds__(kBlock, GS_MIN_BLOCKS) render_fixed_kernel(const __grid_constant__ RenderParams P) {
+	constexpr bool kAdaptive = (kF & 4) != 0;
+	const unsigned long long total_items = kAdaptive ? (unsigned long long)__ldg(P.n_list) * P.sample_count : P.total_items;
 	__shared__ uint8_t s_perm[256];
 	__shared__ float4 s_top[kTopNodes > 0 ? kTopNodes * 4 : 1];
 	if (kTopNodes > 0)
@@ -68,6 +71,7 @@ __global__ void __launch_bounds__(kBlock, GS_MIN_BLOCKS) render_fixed_kernel(con
 	// its "no more chunks" flag (warp-uniform).  2.6 KB per CTA; parking the whole path state the same way (12 KB) was
 	// measured slower -- the L1 capacity it takes away costs more than the spills it saves.
 	__shared__ float s_sum[4][kBlock];
+	__shared__ double s_lum[kAdaptive ? 2 : 1][kAdaptive ? kBlock : 1];  // adaptive: the lane's share of sum, sq_sum (f64 like the reference)
 	__shared__ uint32_t s_pix[kBlock];
 	__shared__ unsigned long long s_chunk[kBlock / 32][3];
 	unsigned long long* const chunk = s_chunk[threadIdx.x >> 5];
@@ -77,16 +81,28 @@ __global__ void __launch_bounds__(kBlock, GS_MIN_BLOCKS) render_fixed_kernel(con
 
 	auto flush_pixel = [&]() {
 		const unsigned t = threadIdx.x;
-		if (s_pix[t] != 0xffffffffu) red_add_v4(P.accum + s_pix[t], s_sum[0][t], s_sum[1][t], s_sum[2][t], s_sum[3][t]);
+		if (s_pix[t] != 0xffffffffu) {
+			red_add_v4(P.accum + s_pix[t], s_sum[0][t], s_sum[1][t], s_sum[2][t], s_sum[3][t]);
+			if (kAdaptive) { atomicAdd(&P.lum[s_pix[t]].x, s_lum[0][t]); atomicAdd(&P.lum[s_pix[t]].y, s_lum[1][t]); }
+		}
 	};
 	auto finish_path = [&]() {  // pixel_color += sample_color, camera.rs:141
 		const unsigned t = threadIdx.x;
 		float ar = st.L.x, ag = st.L.y, ab = st.L.z, an = 1.f;
+		double lum = 0.0, lum_sq = 0.0;
+		if (kAdaptive) {  // color::luminance, color.rs:31-33 (0.144 sic)
+			lum = 0.299 * (double)st.L.x + 0.587 * (double)st.L.y + 0.144 * (double)st.L.z;
+			lum_sq = lum * lum;
+		}
 		if (st.pixel() != s_pix[t]) {
 			flush_pixel();
 			s_pix[t] = st.pixel();
-		} else { ar += s_sum[0][t]; ag += s_sum[1][t]; ab += s_sum[2][t]; an += s_sum[3][t]; }
+		} else {
+			ar += s_sum[0][t]; ag += s_sum[1][t]; ab += s_sum[2][t]; an += s_sum[3][t];
+			if (kAdaptive) { lum += s_lum[0][t]; lum_sq += s_lum[1][t]; }
+		}
 		s_sum[0][t] = ar; s_sum[1][t] = ag; s_sum[2][t] = ab; s_sum[3][t] = an;
+		if (kAdaptive) { s_lum[0][t] = lum; s_lum[1][t] = lum_sq; }
 		state = kDead;
 	};
 
@@ -111,16 +127,17 @@ __global__ void __launch_bounds__(kBlock, GS_MIN_BLOCKS) render_fixed_kernel(con
 					unsigned long long base = 0;
 					if (lane == 0) base = atomicAdd(P.work_counter, (unsigned long long)P.chunk);
 					base = __shfl_sync(kFull, base, 0);
-					if (base >= P.total_items) exhausted = true;
-					else { warp_next = base; warp_end = min(base + (unsigned long long)P.chunk, P.total_items); }
+					if (base >= total_items) exhausted = true;
+					else { warp_next = base; warp_end = min(base + (unsigned long long)P.chunk, total_items); }
 				}
 				const unsigned long long avail = warp_end - warp_next;
 				if (state == kDead) {
 					const unsigned rank = __popc(dead & lt_mask);
 					if (rank < avail) {
 						const unsigned long long item = warp_next + rank;
-						const uint32_t pixel = (uint32_t)(item / P.sample_count);
+						uint32_t pixel = (uint32_t)(item / P.sample_count);
 						const uint32_t sample = (uint32_t)(item % P.sample_count) + P.sample_begin;
+						if (kAdaptive) pixel = __ldg(P.pixel_list + pixel);
 						path_begin(st, P.cam, P.seed, pixel, sample);
 						state = kSetup;
 					}
@@ -221,67 +238,50 @@ __global__ void __launch_bounds__(kBlock, GS_MIN_BLOCKS) render_fixed_kernel(con
 	flush_pixel();
 	// every work item starts exactly one path: no per-lane counter for them
 	flush_stats(P.stats, pc, 0u);
-	if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(P.stats + 1, P.total_items);
+	if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(P.stats + 1, total_items);
 }
 
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
-	return v;
+// ---- the adaptive sampler's control flow, camera.rs:125-171 ------------------------------------------------------
+// Camera::sample loops per pixel: take batch_size samples, test the luminance statistics, stop or take another batch.
+// On the device the loop is turned inside out: ONE launch of the fixed-count megakernel per batch over the list of
+// pixels still sampling (same (pixel, global sample index) Philox streams, so every pixel sees exactly the samples the
+// per-pixel loop would give it), then this kernel applies the reference's stop test to each of them and writes the
+// list for the next batch.  The per-pixel state is the accumulator (sum rgb, n) plus (sum lum, sum lum^2) in f64.
+__global__ void adaptive_init_kernel(uint32_t* __restrict__ list, unsigned* __restrict__ n_list, unsigned pixel_begin, unsigned pixel_stride,
+                                     unsigned n_pixels) {
+	const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k < n_pixels) list[k] = pixel_begin + k * pixel_stride;
+	if (k == 0) { n_list[0] = n_pixels; n_list[1] = 0u; }
 }
 
-__global__ void __launch_bounds__(kBlock) render_adaptive_kernel(const __grid_constant__ AdaptiveParams P) {
-	__shared__ uint8_t s_perm[256];
-	load_perm(s_perm, P.sc.perlin_perm);
+__global__ void adaptive_decide_kernel(const uint32_t* __restrict__ list, const unsigned* __restrict__ n_in, uint32_t* __restrict__ next,
+                                       unsigned* __restrict__ n_out, const float4* __restrict__ accum, const double2* __restrict__ lum,
+                                       double confidence_sq, double tolerance_sq, unsigned max_samples) {
+	const unsigned n = *n_in;
 	const unsigned lane = threadIdx.x & 31u;
-	const unsigned lt_mask = (1u << lane) - 1u;
-	PathCounters pc = {0u, 0u, 0u};
-	unsigned paths = 0;
-	for (;;) {
-		unsigned long long k = 0;
-		if (lane == 0) k = atomicAdd(P.work_counter, 1ull);
-		k = __shfl_sync(kFull, k, 0);
-		if (k >= P.n_pixels) break;
-		const uint32_t pixel = P.pixel_begin + (uint32_t)k * P.pixel_stride;
-		double sum = 0.0, sq_sum = 0.0, cr = 0.0, cg = 0.0, cb = 0.0;  // this lane's share of camera.rs:131-133
-		double sample_count = 0.0;
-		unsigned next = 0;
-		for (;;) {
-			sample_count += (double)P.batch_size;  // camera.rs:137
-			const unsigned end = next + P.batch_size;
-			PathState st;
-			bool alive = false;
-			for (;;) {  // one batch, samples spread over the lanes with regeneration inside the batch
-				const unsigned dead = __ballot_sync(kFull, !alive);
-				if (dead) {
-					const unsigned avail = end - next;
-					if (!alive) {
-						const unsigned rank = __popc(dead & lt_mask);
-						if (rank < avail) { path_begin(st, P.cam, P.seed, pixel, next + rank); alive = true; ++paths; }
-					}
-					const unsigned need = __popc(dead);
-					next += need < avail ? need : avail;
-				}
-				if (!__any_sync(kFull, alive)) break;
-				if (alive && path_step<2>(P.sc, P.cam, s_perm, st, pc)) {
-					cr += (double)st.L.x; cg += (double)st.L.y; cb += (double)st.L.z;
-					const double lum = 0.299 * (double)st.L.x + 0.587 * (double)st.L.y + 0.144 * (double)st.L.z;  // color.rs:31-33
-					sum += lum; sq_sum += lum * lum;
-					alive = false;
-				}
-			}
-			const double tsum = warp_sum(sum), tsq = warp_sum(sq_sum);
-			const double mean = tsum / sample_count;  // camera.rs:150-158
-			const double variance_sq = 1.0 / (sample_count - 1.0) * (tsq - tsum * tsum / sample_count);
-			const double convergence_sq = P.confidence_sq * variance_sq / sample_count;
-			if (convergence_sq < mean * mean * P.tolerance_sq) break;
+	for (unsigned base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += gridDim.x * blockDim.x) {
+		const unsigned k = base + lane;
+		bool more = false;
+		uint32_t pixel = 0;
+		if (k < n) {
+			pixel = list[k];
+			const double sample_count = (double)accum[pixel].w;  // exact: one 1.0f per path, far below 2^24
+			const double2 s = lum[pixel];
+			const double mean = s.x / sample_count;  // camera.rs:150-158
+			const double variance_sq = 1.0 / (sample_count - 1.0) * (s.y - s.x * s.x / sample_count);
+			const double convergence_sq = confidence_sq * variance_sq / sample_count;
+			const bool converged = convergence_sq < mean * mean * tolerance_sq;
 			const unsigned sc_u32 = sample_count >= 4294967295.0 ? 4294967295u : (unsigned)sample_count;
-			if (sc_u32 > P.max_samples) break;  // camera.rs:162-164
+			more = !converged && !(sc_u32 > max_samples);  // camera.rs:162-164
 		}
-		const double tr = warp_sum(cr), tg = warp_sum(cg), tb = warp_sum(cb);
-		if (lane == 0) P.accum[pixel] = make_float4((float)tr, (float)tg, (float)tb, (float)sample_count);
+		const unsigned m = __ballot_sync(kFull, more);  // one atomic per warp; the order of the list does not matter
+		if (m) {
+			unsigned slot = 0;
+			if (lane == 0) slot = atomicAdd(n_out, (unsigned)__popc(m));
+			slot = __shfl_sync(kFull, slot, 0);
+			if (more) next[slot + __popc(m & ((1u << lane) - 1u))] = pixel;
+		}
 	}
-	flush_stats(P.stats, pc, paths);
 }
 
 // pixel_color /= sample_count (camera.rs:167)
@@ -341,40 +341,55 @@ __global__ void __launch_bounds__(kBlock) path_radiance_kernel(const __grid_cons
 template <int kF>
 static void fixed_occupancy(int* n) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(n, render_fixed_kernel<kF>, kBlock, 0); }
 
-int render_fixed_blocks_per_sm(bool count_nodes, bool triangles) {
+// kernel variant: bit 0 = count node visits, bit 1 = triangles, bit 2 = adaptive batch (never combined with bit 0)
+static int fixed_variant(const RenderParams& p, bool count_nodes, bool triangles) {
+	if (p.pixel_list) return 4 | (triangles ? 2 : 0);
+	return (count_nodes ? 1 : 0) | (triangles ? 2 : 0);
+}
+
+static int fixed_blocks_per_sm(int variant) {
 	int n = 0;
-	switch ((count_nodes ? 1 : 0) | (triangles ? 2 : 0)) {
+	switch (variant) {
 		case 0: fixed_occupancy<0>(&n); break;
 		case 1: fixed_occupancy<1>(&n); break;
 		case 2: fixed_occupancy<2>(&n); break;
-		default: fixed_occupancy<3>(&n); break;
+		case 3: fixed_occupancy<3>(&n); break;
+		case 4: fixed_occupancy<4>(&n); break;
+		default: fixed_occupancy<6>(&n); break;
 	}
 	return n > 0 ? n : 1;
 }
 
+int render_fixed_blocks_per_sm(bool count_nodes, bool triangles) { return fixed_blocks_per_sm((count_nodes ? 1 : 0) | (triangles ? 2 : 0)); }
+
 cudaError_t launch_render_fixed(const RenderParams& p, int sm_count, bool count_nodes, bool triangles, cudaStream_t stream) {
-	const int per_sm = render_fixed_blocks_per_sm(count_nodes, triangles);
-	unsigned long long warps_needed = (p.total_items + 31ull) / 32ull;
+	const int variant = fixed_variant(p, count_nodes, triangles);
+	const int per_sm = fixed_blocks_per_sm(variant);
+	unsigned long long warps_needed = (p.total_items + 31ull) / 32ull;  // adaptive: total_items = the upper bound (every listed pixel)
 	unsigned long long blocks_needed = (warps_needed + (kBlock / 32) - 1) / (kBlock / 32);
 	unsigned long long grid = (unsigned long long)sm_count * per_sm;  // persistent: SMs x resident CTAs
 	if (blocks_needed < grid) grid = blocks_needed ? blocks_needed : 1;
-	switch ((count_nodes ? 1 : 0) | (triangles ? 2 : 0)) {
+	switch (variant) {
 		case 0: render_fixed_kernel<0><<<(unsigned)grid, kBlock, 0, stream>>>(p); break;
 		case 1: render_fixed_kernel<1><<<(unsigned)grid, kBlock, 0, stream>>>(p); break;
 		case 2: render_fixed_kernel<2><<<(unsigned)grid, kBlock, 0, stream>>>(p); break;
-		default: render_fixed_kernel<3><<<(unsigned)grid, kBlock, 0, stream>>>(p); break;
+		case 3: render_fixed_kernel<3><<<(unsigned)grid, kBlock, 0, stream>>>(p); break;
+		case 4: render_fixed_kernel<4><<<(unsigned)grid, kBlock, 0, stream>>>(p); break;
+		default: render_fixed_kernel<6><<<(unsigned)grid, kBlock, 0, stream>>>(p); break;
 	}
 	return cudaGetLastError();
 }
 
-cudaError_t launch_render_adaptive(const AdaptiveParams& p, int sm_count, cudaStream_t stream) {
-	int per_sm = 0;
-	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_adaptive_kernel, kBlock, 0);
-	if (per_sm < 1) per_sm = 1;
-	unsigned long long blocks_needed = ((unsigned long long)p.n_pixels + (kBlock / 32) - 1) / (kBlock / 32);
-	unsigned long long grid = (unsigned long long)sm_count * per_sm;
-	if (blocks_needed < grid) grid = blocks_needed ? blocks_needed : 1;
-	render_adaptive_kernel<<<(unsigned)grid, kBlock, 0, stream>>>(p);
+cudaError_t launch_adaptive_init(uint32_t* list, unsigned* n_list, unsigned pixel_begin, unsigned pixel_stride, unsigned n_pixels, cudaStream_t stream) {
+	adaptive_init_kernel<<<(n_pixels + 255) / 256, 256, 0, stream>>>(list, n_list, pixel_begin, pixel_stride, n_pixels);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_adaptive_decide(const AdaptiveParams& p, const uint32_t* list, const unsigned* n_in, uint32_t* next, unsigned* n_out,
+                                   const double2* lum, cudaStream_t stream) {
+	const unsigned blocks = (p.n_pixels + 255) / 256;
+	adaptive_decide_kernel<<<blocks < 1184u ? (blocks ? blocks : 1u) : 1184u, 256, 0, stream>>>(list, n_in, next, n_out, p.accum, lum, p.confidence_sq,
+	                                                                                          p.tolerance_sq, p.max_samples);
 	return cudaGetLastError();
 }
 
