@@ -246,11 +246,15 @@ int gs_render_accumulate(gs_scene* scene, const gs_camera* camera, uint64_t seed
                          uint32_t sample_count, void* d_accum, void* cuda_stream);
 /* The adaptive sampler of Camera::sample (camera.rs:125-171) with the reference's batch / stop-test
  * semantics, for pixels pixel_begin, pixel_begin + pixel_stride, ... (ranks interleave pixels; every
- * pixel's whole batch loop runs on one GPU).  Writes (sum r, sum g, sum b, count) into d_accum[pixel]. */
+ * pixel's whole batch loop runs on one GPU).  Leaves (sum r, sum g, sum b, count) in d_accum[pixel]; the entries
+ * of these pixels must be ZERO on entry (the count doubles as the sampler's running sample_count).  Runs one
+ * launch per batch over the pixels still sampling and reads back a 4-byte "any left?" after batches 1, 2, 4, ...:
+ * it synchronises `cuda_stream` a few times and has finished issuing work when it returns. */
 int gs_render_adaptive_accumulate(gs_scene* scene, const gs_camera* camera, const gs_sample_settings* settings,
                                   uint64_t seed, uint32_t pixel_begin, uint32_t pixel_stride, void* d_accum,
                                   void* cuda_stream);
-/* Options: "count_nodes" (0/1) switches to the kernel variant that counts BVH node fetches. */
+/* Options: "count_nodes" (0/1) switches to the kernel variant that counts BVH node fetches and texel reads;
+ * "wavefront" (0/1) selects the wavefront pipeline for fixed-count renders; "pool_capacity" its path pool size. */
 int gs_scene_set_option(gs_scene* scene, const char* key, int64_t value);
 /* d_accum (device, W*H float4) -> host mean radiance and counts; blocking on `cuda_stream`. */
 int gs_resolve(gs_scene* scene, const void* d_accum, int32_t width, int32_t height, float* out_rgb,

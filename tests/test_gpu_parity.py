@@ -223,7 +223,7 @@ def test_same_seed_cornell_image_is_the_oracle_image():
 
 
 def test_adaptive_sampler_matches_the_reference_semantics():
-    """Camera::sample's batch loop (camera.rs:125-171, Q3-Q5) on the device, one warp per pixel"""
+    """Camera::sample's batch loop (camera.rs:125-171, Q3-Q5) on the device: one megakernel launch per batch over the pixels still sampling + the stop test"""
     kw = dict(width=96)
     host = gs.HostScene.build("scene6", **kw)          # cornell_box with its own settings {.95, .5, 32, 1000}
     dev = gs.DeviceScene(host)
@@ -461,3 +461,26 @@ def test_scene_create_destroy_reuses_device_memory():
             assert np.allclose(rgb, first, rtol=1e-4, atol=1e-6)
     torch.cuda.synchronize()
     assert free0 - torch.cuda.mem_get_info()[0] < (8 << 20), "creating and destroying scenes keeps taking device memory"
+
+
+def test_adaptive_pixel_split_equals_the_single_gpu_render():
+    """Multi-GPU adaptive sampling: rank g of G takes pixels g, g+G, ... (each pixel's whole batch loop stays on one GPU)
+    into its own zeroed accumulator; the sum of the accumulators is the single-GPU result (same samples per pixel, so
+    identical counts and, up to the order of float additions, identical sums)."""
+    import torch
+
+    host = gs.HostScene.build("scene6", width=72)   # Cornell box, {.95, .5, 32, 1000}
+    dev = gs.DeviceScene(host)
+    n = dev.width * dev.height
+    whole = torch.zeros((n, 4), device="cuda")
+    dev.render_adaptive_accumulate(whole.data_ptr(), seed=6)
+    parts = torch.zeros((3, n, 4), device="cuda")
+    for g in range(3):
+        dev.render_adaptive_accumulate(parts[g].data_ptr(), seed=6, pixel_begin=g, pixel_stride=3)
+    torch.cuda.synchronize()
+    # disjoint tiles: a pixel is non-zero in exactly one part
+    assert int(((parts[:, :, 3] > 0).sum(dim=0) != 1).sum()) == 0
+    merged = parts.sum(dim=0)
+    assert torch.equal(merged[:, 3], whole[:, 3])
+    assert 32 <= float(whole[:, 3].min()) and float(whole[:, 3].max()) <= 1024
+    assert torch.allclose(merged[:, :3], whole[:, :3], rtol=1e-4, atol=1e-5)
