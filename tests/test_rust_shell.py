@@ -1,0 +1,86 @@
+"""The Rust crate shell (rust/) cannot be compiled here (no Rust toolchain), so its FFI declarations are kept in
+lock-step with include/grayshift.h mechanically: every function of the header is declared in rust/src/ffi.rs with the
+same number of parameters, and every #[repr(C)] struct lists the fields of its ctypes twin (grayshift_b200/ffi.py, whose
+layout tests/test_abi.py checks against the C compiler) in the same order with the corresponding types."""
+import ctypes as C
+import os
+import re
+
+from grayshift_b200 import ffi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = open(os.path.join(ROOT, "include", "grayshift.h")).read()
+RUST = open(os.path.join(ROOT, "rust", "src", "ffi.rs")).read()
+
+
+def _strip_comments(text):
+    return re.sub(r"//[^\n]*", "", re.sub(r"/\*.*?\*/", "", text, flags=re.S))
+
+
+def _params(arglist):
+    arglist = arglist.strip()
+    return 0 if arglist in ("", "void") else len([a for a in arglist.split(",") if a.strip()])
+
+
+def header_functions():
+    h = _strip_comments(HEADER)
+    return {m.group(1): _params(m.group(2)) for m in re.finditer(r"\b(gs_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", h)}
+
+
+def rust_functions():
+    r = _strip_comments(RUST)
+    block = r[r.index('extern "C" {'):]
+    return {m.group(1): _params(m.group(2)) for m in re.finditer(r"pub fn (gs_[a-z0-9_]+)\s*\(([^)]*)\)", block)}
+
+
+def rust_structs():
+    r = _strip_comments(RUST)
+    out = {}
+    for m in re.finditer(r"#\[repr\(C\)\][^{]*?pub struct (gs_[a-z_]+)\s*\{(.*?)\}", r, flags=re.S):
+        out[m.group(1)] = [(f.group(1), f.group(2).strip()) for f in re.finditer(r"pub (\w+)\s*:\s*([^,\n]+),", m.group(2))]
+    return out
+
+
+# (c_uint64 and c_size_t are one ctypes type on LP64: either Rust spelling has the right size; the names are checked too)
+RUST_TYPE = {C.c_double: {"f64"}, C.c_int32: {"i32"}, C.c_uint32: {"u32"}, C.c_uint64: {"u64", "usize"}, ffi.d3: {"[f64; 3]"}}
+
+
+def test_every_header_function_is_declared_in_the_rust_ffi_with_the_same_arity():
+    h, r = header_functions(), rust_functions()
+    assert set(h) == set(ffi.CUDA_SYMBOLS), "header and ctypes table differ"
+    assert set(h) == set(r), f"missing in ffi.rs: {sorted(set(h) - set(r))}; unknown: {sorted(set(r) - set(h))}"
+    for name, n in h.items():
+        assert r[name] == n, f"{name}: header takes {n} parameters, ffi.rs declares {r[name]}"
+        assert len(ffi.CUDA_SYMBOLS[name][1]) == n, f"{name}: ctypes argtypes out of step"
+
+
+def test_rust_struct_fields_follow_the_c_layout():
+    rs = rust_structs()
+    for name in ("gs_sphere", "gs_quad", "gs_triangle", "gs_bvh_node", "gs_medium", "gs_material", "gs_texture", "gs_image",
+                 "gs_scene_desc", "gs_camera", "gs_sample_settings", "gs_stats"):
+        ct = getattr(ffi, name)
+        assert name in rs, f"ffi.rs lacks #[repr(C)] struct {name}"
+        fields = rs[name]
+        assert [f for f, _ in fields] == [f for f, _ in ct._fields_], f"{name}: field names / order differ"
+        for (fname, rtype), (_, ctype) in zip(fields, ct._fields_):
+            if ctype in RUST_TYPE:
+                assert rtype in RUST_TYPE[ctype], f"{name}.{fname}: {rtype} vs {ctype.__name__}"
+            else:  # pointers
+                assert rtype.startswith("*const") or rtype.startswith("*mut"), f"{name}.{fname}: expected a pointer, got {rtype}"
+
+
+def test_rust_constants_match_the_header():
+    h = _strip_comments(HEADER)
+    for m in re.finditer(r"pub const (GS_[A-Z0-9_]+): \w+ = (\d+);", RUST):
+        name, value = m.group(1), int(m.group(2))
+        hm = re.search(rf"\b{name}\b\s*=?\s*(\d+)", h)
+        assert hm is not None, f"{name} is not in the header"
+        assert int(hm.group(1)) == value, f"{name}: {value} in ffi.rs, {hm.group(1)} in the header"
+
+
+def test_build_rs_compiles_the_same_translation_units_as_the_makefile():
+    mk = open(os.path.join(ROOT, "grayshift_b200", "csrc", "Makefile")).read()
+    rs = open(os.path.join(ROOT, "rust", "build.rs")).read()
+    units = sorted(set(re.findall(r"(\w+\.cu)\b", mk)))
+    assert units == sorted(set(re.findall(r'"(\w+\.cu)"', rs))), "build.rs and the Makefile list different .cu files"
+    assert "compute_100a,code=sm_100a" in rs and "-fmad=false" in rs
