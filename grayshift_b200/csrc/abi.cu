@@ -795,6 +795,8 @@ int gs_render_adaptive_accumulate(gs_scene* s, const gs_camera* camera, const gs
 	// Camera::sample's loop (camera.rs:135-165) leaves after the first batch that takes `sample_count as u32` past
 	// max_samples: at most max_samples / batch_size + 1 batches.
 	const unsigned long long rounds = (unsigned long long)settings->max_samples / settings->batch_size + 1ull;
+	// the per-pixel sample count lives in the accumulator's fourth float: exact up to 2^24
+	if (rounds * settings->batch_size > (1ull << 24)) return fail(GS_ERR_UNSUPPORTED, "adaptive sampling beyond 2^24 samples per pixel");
 	GS_CUDA(s->px_list[0].alloc(n_pixels)); GS_CUDA(s->px_list[1].alloc(n_pixels));
 	GS_CUDA(s->px_count.alloc(2));
 	GS_CUDA(s->lum.alloc(total));
