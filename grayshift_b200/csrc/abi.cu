@@ -73,6 +73,7 @@ template <class T> struct DevBuf {
 };
 
 constexpr int kCounterSlots = 64;
+constexpr unsigned kAdaptiveTailPixels = 2048;  // adaptive renders: below this many unfinished pixels, switch to one warp per pixel
 constexpr int kStatSlots = 16;  // [0..3] = gs_stats totals; [4..] only written by the GS_DIVERGENCE_STATS diagnostic build
 
 }  // namespace
@@ -828,6 +829,19 @@ int gs_render_adaptive_accumulate(gs_scene* s, const gs_camera* camera, const gs
 			GS_CUDA(cudaMemcpyAsync(&left, s->px_count.p + nxt, sizeof left, cudaMemcpyDeviceToHost, st));
 			GS_CUDA(cudaStreamSynchronize(st));
 			if (left == 0) break;
+			if (left <= kAdaptiveTailPixels) {  // a handful of hard pixels: one warp each finishes them in a single launch
+				AdaptiveTailParams tp;
+				tp.sc = s->ds; tp.cam = p.cam; tp.seed = seed;
+				tp.confidence_sq = ap.confidence_sq; tp.tolerance_sq = ap.tolerance_sq;
+				tp.batch_size = settings->batch_size; tp.max_samples = settings->max_samples;
+				tp.list = s->px_list[nxt].p; tp.n_list = s->px_count.p + nxt;
+				tp.accum = static_cast<float4*>(d_accum); tp.lum = s->lum.p;
+				tp.work_counter = next_counter(s); tp.stats = s->stats.p;
+				GS_CUDA(cudaMemsetAsync(tp.work_counter, 0, sizeof(unsigned long long), st));
+				GS_CUDA(launch_adaptive_tail(tp, left, s->sm_count, st));
+				s->launches += 1;
+				break;
+			}
 		}
 	}
 	return GS_OK;

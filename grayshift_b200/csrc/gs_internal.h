@@ -28,9 +28,24 @@ struct AdaptiveParams {  // the stop test of camera.rs:150-164
 	const float4* accum;
 };
 
+struct AdaptiveTailParams {  // the last few pixels: one warp per pixel runs the rest of its batch loop (adaptive_tail_kernel)
+	DeviceScene sc;
+	DCamera cam;
+	unsigned long long seed;
+	double confidence_sq, tolerance_sq;
+	unsigned batch_size, max_samples;
+	const uint32_t* list;
+	const unsigned* n_list;
+	float4* accum;
+	const double2* lum;
+	unsigned long long* work_counter;
+	unsigned long long* stats;
+};
+
 // launch wrappers (defined next to the kernels); all asynchronous on `stream`
 cudaError_t launch_render_fixed(const RenderParams& p, int sm_count, bool count_nodes, bool triangles, cudaStream_t stream);
 cudaError_t launch_adaptive_init(uint32_t* list, unsigned* n_list, unsigned pixel_begin, unsigned pixel_stride, unsigned n_pixels, cudaStream_t stream);
+cudaError_t launch_adaptive_tail(const AdaptiveTailParams& p, unsigned n_upper, int sm_count, cudaStream_t stream);
 cudaError_t launch_adaptive_decide(const AdaptiveParams& p, const uint32_t* list, const unsigned* n_in, uint32_t* next, unsigned* n_out,
                                    const double2* lum, cudaStream_t stream);
 cudaError_t launch_resolve(const float4* accum, int n_pixels, float* out_rgb, unsigned* out_counts, cudaStream_t stream);

@@ -284,6 +284,73 @@ __global__ void adaptive_decide_kernel(const uint32_t* __restrict__ list, const 
 	}
 }
 
+// The tail of an adaptive render: when only a few pixels are still sampling, a launch per batch costs more than it
+// renders (a batch of 32 samples is one warp's worth of work and a whole launch's worth of latency).  Then one warp
+// takes each remaining pixel and runs the rest of its loop (camera.rs:135-165) on its own, starting from the sums the
+// batch rounds left in accum / lum: the batch's samples spread over the lanes, regeneration inside the batch.
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+	return v;
+}
+
+__global__ void __launch_bounds__(kBlock) adaptive_tail_kernel(const __grid_constant__ AdaptiveTailParams P) {
+	__shared__ uint8_t s_perm[256];
+	load_perm(s_perm, P.sc.perlin_perm);
+	const unsigned lane = threadIdx.x & 31u;
+	const unsigned lt_mask = (1u << lane) - 1u;
+	const unsigned n_list = __ldg(P.n_list);
+	PathCounters pc = {0u, 0u, 0u};
+	unsigned paths = 0;
+	for (;;) {
+		unsigned long long k = 0;
+		if (lane == 0) k = atomicAdd(P.work_counter, 1ull);
+		k = __shfl_sync(kFull, k, 0);
+		if (k >= n_list) break;
+		const uint32_t pixel = P.list[k];
+		const float4 a0 = P.accum[pixel];
+		const double2 l0 = P.lum[pixel];
+		double sum = 0.0, sq_sum = 0.0, cr = 0.0, cg = 0.0, cb = 0.0;  // this lane's share of what is added now
+		double sample_count = (double)a0.w;
+		unsigned next = (unsigned)a0.w;  // global sample index of the next sample of this pixel
+		for (;;) {
+			sample_count += (double)P.batch_size;  // camera.rs:137
+			const unsigned end = next + P.batch_size;
+			PathState st;
+			bool alive = false;
+			for (;;) {
+				const unsigned dead = __ballot_sync(kFull, !alive);
+				if (dead) {
+					const unsigned avail = end - next;
+					if (!alive) {
+						const unsigned rank = __popc(dead & lt_mask);
+						if (rank < avail) { path_begin(st, P.cam, P.seed, pixel, next + rank); alive = true; ++paths; }
+					}
+					const unsigned need = __popc(dead);
+					next += need < avail ? need : avail;
+				}
+				if (!__any_sync(kFull, alive)) break;
+				if (alive && path_step<2>(P.sc, P.cam, s_perm, st, pc)) {
+					cr += (double)st.L.x; cg += (double)st.L.y; cb += (double)st.L.z;
+					const double lum = 0.299 * (double)st.L.x + 0.587 * (double)st.L.y + 0.144 * (double)st.L.z;  // color.rs:31-33
+					sum += lum; sq_sum += lum * lum;
+					alive = false;
+				}
+			}
+			const double tsum = l0.x + warp_sum(sum), tsq = l0.y + warp_sum(sq_sum);
+			const double mean = tsum / sample_count;  // camera.rs:150-158
+			const double variance_sq = 1.0 / (sample_count - 1.0) * (tsq - tsum * tsum / sample_count);
+			const double convergence_sq = P.confidence_sq * variance_sq / sample_count;
+			if (convergence_sq < mean * mean * P.tolerance_sq) break;
+			const unsigned sc_u32 = sample_count >= 4294967295.0 ? 4294967295u : (unsigned)sample_count;
+			if (sc_u32 > P.max_samples) break;  // camera.rs:162-164
+		}
+		const double tr = warp_sum(cr), tg = warp_sum(cg), tb = warp_sum(cb);
+		if (lane == 0) P.accum[pixel] = make_float4(a0.x + (float)tr, a0.y + (float)tg, a0.z + (float)tb, (float)sample_count);
+	}
+	flush_stats(P.stats, pc, paths);
+}
+
 // pixel_color /= sample_count (camera.rs:167)
 __global__ void resolve_kernel(const float4* __restrict__ accum, int n_pixels, float* __restrict__ out_rgb, unsigned* __restrict__ out_counts) {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -382,6 +449,17 @@ cudaError_t launch_render_fixed(const RenderParams& p, int sm_count, bool count_
 
 cudaError_t launch_adaptive_init(uint32_t* list, unsigned* n_list, unsigned pixel_begin, unsigned pixel_stride, unsigned n_pixels, cudaStream_t stream) {
 	adaptive_init_kernel<<<(n_pixels + 255) / 256, 256, 0, stream>>>(list, n_list, pixel_begin, pixel_stride, n_pixels);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_adaptive_tail(const AdaptiveTailParams& p, unsigned n_upper, int sm_count, cudaStream_t stream) {
+	int per_sm = 0;
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, adaptive_tail_kernel, kBlock, 0);
+	if (per_sm < 1) per_sm = 1;
+	unsigned long long blocks_needed = ((unsigned long long)n_upper + (kBlock / 32) - 1) / (kBlock / 32);
+	unsigned long long grid = (unsigned long long)sm_count * per_sm;
+	if (blocks_needed < grid) grid = blocks_needed ? blocks_needed : 1;
+	adaptive_tail_kernel<<<(unsigned)grid, kBlock, 0, stream>>>(p);
 	return cudaGetLastError();
 }
 
