@@ -5,10 +5,11 @@
 //   paths; a lane whose path ends takes the next (pixel, sample) item at the top of the next
 //   iteration (path regeneration), so the warp stays full until the whole image is exhausted.
 //   Work items are handed out in chunks through one global 64-bit atomic per warp per chunk.
-//   Each lane keeps (sum r, sum g, sum b, n) for its current pixel in registers and flushes with one
+//   Each lane keeps (sum r, sum g, sum b, n) for its current pixel in shared memory and flushes with one
 //   128-bit vector reduction (red.global.add.v4.f32) when its pixel changes.
 // adaptive sampling (camera.rs:125-171, exact batch / stop-test semantics, Q3-Q5): one launch of the same megakernel per
-//   batch over the pixels still sampling + adaptive_decide_kernel (the stop test), see below.
+//   batch over the pixels still sampling + adaptive_decide_kernel (the stop test); adaptive_tail_kernel (one warp per
+//   pixel) for the last few pixels.  See below.
 // Grids are sized to SM count x resident CTAs (persistent), never to the image.
 #include "gs_internal.h"
 #include "gs_kernel_util.cuh"
@@ -23,7 +24,8 @@ namespace gs {
 //            lanes have finished (or nobody is traversing): the others KEEP their traversal state (node, sp,
 //            closest hit, stack) and continue in the next phase B.
 enum LaneState : int { kDead = 0, kTraverse = 1, kShade = 2, kSetup = 3 };
-// Tuning knobs (overridable with -D for the A/B sweeps of scripts/gpu_sweep.sh; defaults = the measured best).
+// Tuning knobs (overridable with -D for the A/B sweeps of scripts/build_variants.sh + scripts/gpu_ab.sh; defaults = the
+// measured best, profiles/r01_v5_variant_sweeps.log).
 #ifndef GS_MIN_SHADE
 #define GS_MIN_SHADE 24   // leave phase B once this many lanes have finished their ray (32 = classic while-while, every ray to completion)
 #endif
@@ -35,7 +37,8 @@ enum LaneState : int { kDead = 0, kTraverse = 1, kShade = 2, kSetup = 3 };
                           // registers -> 1403.  profiles/r01_v5_variant_sweeps.log
 #endif
 #ifndef GS_TOP_SMEM
-#define GS_TOP_SMEM 0     // nodes of the top BVH levels (breadth-first prefix) staged in shared memory per CTA; 0 = off
+#define GS_TOP_SMEM 0     // nodes of the top BVH levels (breadth-first prefix) staged in shared memory per CTA; 0 = off.  Measured -9 %
+                          // with 64 or 256 nodes: the top of the tree is L1-resident anyway and shared memory takes L1 capacity away
 #endif
 constexpr int kTopNodes = GS_TOP_SMEM;
 static_assert(kTopNodes <= kNodePad, "gs_scene_create pads the node array to kNodePad entries");
@@ -65,7 +68,7 @@ __global__ void __launch_bounds__(kBlock, GS_MIN_BLOCKS) render_fixed_kernel(con
 	tv.node = kStackSentinel; tv.sp = 0;
 	int seg_medium = -1;
 	int stack[kMaxStack];
-	// The kernel is register-bound (80 registers = 24 warps per SM), so what is touched once per PATH lives in shared
+	// The kernel is register-bound (96 registers = 20 warps per SM), so what is touched once per PATH lives in shared
 	// memory instead of in registers held through every traversal: the lane's running sum for its current pixel
 	// (float4 + pixel id, [field][thread]: conflict-free) and the warp's current chunk of work items [next, end) with
 	// its "no more chunks" flag (warp-uniform).  2.6 KB per CTA; parking the whole path state the same way (12 KB) was
