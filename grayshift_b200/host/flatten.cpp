@@ -10,11 +10,19 @@
 //     available with FlattenOptions::reference_tree for A/B measurements);
 //  5. materials / textures / images deduplicated by pointer identity (one row per shared Arc).
 #include <algorithm>
+#include <atomic>
 #include <cfloat>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <map>
+#include <mutex>
 #include <stdexcept>
+#include <thread>
+#include <unordered_map>
 
 #include "grayshift.hpp"
 
@@ -32,8 +40,8 @@ struct Xform {
 
 struct Flattener {
 	FlatScene& out;
-	std::map<const Material*, int> mat_ids;
-	std::map<const Texture*, int> tex_ids;
+	std::unordered_map<const Material*, int> mat_ids;  // Arc sharing -> one table row (a scene may hold a material per primitive)
+	std::unordered_map<const Texture*, int> tex_ids;
 	int next_order = 0;
 	std::vector<double> bounds;  // per surface primitive ref: min xyz, max xyz
 	std::vector<uint32_t> refs;  // parallel to bounds
@@ -278,8 +286,6 @@ void build_bvh_sah(const std::vector<double>& bounds, int max_leaf_size, std::ve
 	for (size_t i = 0; i < n; ++i) order[i] = (uint32_t)i;
 	std::vector<double> cent(n * 3);
 	for (size_t i = 0; i < n; ++i) for (int a = 0; a < 3; ++a) cent[i * 3 + a] = 0.5 * (bounds[i * 6 + a] + bounds[i * 6 + 3 + a]);
-	nodes.clear();
-	nodes.reserve(2 * n);
 	constexpr int kBins = 16;
 	constexpr int kMaxDepth = 56;  // device traversal stack is 64 entries
 
@@ -294,12 +300,13 @@ void build_bvh_sah(const std::vector<double>& bounds, int max_leaf_size, std::ve
 		}
 	};
 
+	// Nodes are allocated from a pre-sized array with an atomic counter, so subtrees can be built by several threads
+	// (a tree over n primitives with single-primitive leaves has at most 2n - 1 nodes).  One task = one node: bound it,
+	// pick the SAH split, partition its range of `order` in place, allocate the two children.
 	struct Task { size_t lo, hi; int node, depth; };
-	std::vector<Task> stack;
-	nodes.emplace_back();
-	stack.push_back({0, n, 0, 0});
-	while (!stack.empty()) {
-		Task tk = stack.back(); stack.pop_back();
+	nodes.assign(2 * n, gs_bvh_node{});
+	std::atomic<int> next_node{1};
+	auto process = [&](const Task& tk, std::vector<Task>& out) {
 		const size_t lo = tk.lo, hi = tk.hi, cnt = hi - lo;
 		Box box, cbox;
 		for (size_t k = lo; k < hi; ++k) {
@@ -310,7 +317,7 @@ void build_bvh_sah(const std::vector<double>& bounds, int max_leaf_size, std::ve
 		gs_bvh_node nd{};
 		for (int a = 0; a < 3; ++a) { nd.bounds_min[a] = box.mn[a]; nd.bounds_max[a] = box.mx[a]; }
 		auto make_leaf = [&]() { nd.first_ref = (int)lo; nd.ref_count = (int)cnt; nodes[tk.node] = nd; };
-		if (cnt == 1) { make_leaf(); continue; }
+		if (cnt == 1) { make_leaf(); return; }
 
 		size_t mid = lo;
 		bool split_found = false;
@@ -356,7 +363,7 @@ void build_bvh_sah(const std::vector<double>& bounds, int max_leaf_size, std::ve
 			}
 		}
 		if (!split_found) {
-			if (cnt <= (size_t)max_leaf_size) { make_leaf(); continue; }
+			if (cnt <= (size_t)max_leaf_size) { make_leaf(); return; }
 			// coincident centroids or depth guard: median split by index along the widest centroid axis
 			int axis = 0;
 			double e0 = cbox.mx[0] - cbox.mn[0], e1 = cbox.mx[1] - cbox.mn[1], e2 = cbox.mx[2] - cbox.mn[2];
@@ -365,11 +372,64 @@ void build_bvh_sah(const std::vector<double>& bounds, int max_leaf_size, std::ve
 			std::nth_element(order.begin() + lo, order.begin() + mid, order.begin() + hi,
 			                 [&](uint32_t p, uint32_t q) { return cent[p * 3 + axis] < cent[q * 3 + axis]; });
 		}
-		nd.left = (int)nodes.size(); nodes.emplace_back();
-		nd.right = (int)nodes.size(); nodes.emplace_back();
+		nd.left = next_node.fetch_add(2);
+		nd.right = nd.left + 1;
 		nodes[tk.node] = nd;
-		stack.push_back({mid, hi, nd.right, tk.depth + 1});
-		stack.push_back({lo, mid, nd.left, tk.depth + 1});
+		out.push_back({mid, hi, nd.right, tk.depth + 1});
+		out.push_back({lo, mid, nd.left, tk.depth + 1});
+	};
+
+	unsigned threads = std::thread::hardware_concurrency();
+	if (const char* e = std::getenv("GSH_BUILD_THREADS")) threads = (unsigned)std::max(1, std::atoi(e));
+	threads = std::min(threads, 16u);
+	const bool parallel = threads > 1 && n >= (std::getenv("GSH_BUILD_THREADS") ? 64u : 50000u);
+	std::vector<Task> open{{0, n, 0, 0}};
+	if (parallel) {
+		// the top of the tree on this thread, widest task first, until there are enough subtrees to hand out
+		while (open.size() < 8u * threads) {
+			size_t big = 0;
+			for (size_t i = 1; i < open.size(); ++i) if (open[i].hi - open[i].lo > open[big].hi - open[big].lo) big = i;
+			if (open[big].hi - open[big].lo <= 4096) break;
+			const Task tk = open[big];
+			open.erase(open.begin() + (long)big);
+			process(tk, open);
+		}
+		std::atomic<size_t> next_task{0};
+		std::vector<std::thread> pool;
+		std::exception_ptr failure;
+		std::mutex failure_lock;
+		for (unsigned t = 0; t < threads; ++t)
+			pool.emplace_back([&]() {
+				try {
+					std::vector<Task> stack;
+					for (size_t i; (i = next_task.fetch_add(1)) < open.size();) {
+						stack.assign(1, open[i]);
+						while (!stack.empty()) { const Task tk = stack.back(); stack.pop_back(); process(tk, stack); }
+					}
+				} catch (...) { std::lock_guard<std::mutex> g(failure_lock); failure = std::current_exception(); }
+			});
+		for (auto& th : pool) th.join();
+		if (failure) std::rethrow_exception(failure);
+	} else {
+		while (!open.empty()) { const Task tk = open.back(); open.pop_back(); process(tk, open); }
+	}
+	nodes.resize((size_t)next_node.load());
+	if (parallel) {
+		// the allocation order depends on thread timing: renumber in depth-first pre-order (children after their parent,
+		// as gs_scene_create requires) so that the same input always gives the same array
+		std::vector<gs_bvh_node> sorted;
+		sorted.reserve(nodes.size());
+		std::vector<std::pair<int, int>> dfs{{0, -1}};  // (old index, parent's new index; the right child is pushed first)
+		std::vector<int> renamed(nodes.size(), -1);
+		while (!dfs.empty()) {
+			const int old = dfs.back().first;
+			dfs.pop_back();
+			renamed[old] = (int)sorted.size();
+			sorted.push_back(nodes[old]);
+			if (nodes[old].ref_count == 0) { dfs.push_back({nodes[old].right, 0}); dfs.push_back({nodes[old].left, 0}); }
+		}
+		for (auto& nd : sorted) if (nd.ref_count == 0) { nd.left = renamed[nd.left]; nd.right = renamed[nd.right]; }
+		nodes.swap(sorted);
 	}
 }
 
@@ -406,16 +466,28 @@ void FlatScene::finish() {
 std::unique_ptr<FlatScene> flatten(const HittablePtr& world, const FlattenOptions& opt) {
 	if (!world) throw std::runtime_error("flatten: null world");
 	auto flat = std::make_unique<FlatScene>();
+	// GSH_TRACE=1: stage times on stderr
+	const bool trace = std::getenv("GSH_TRACE") != nullptr;
+	auto t_prev = std::chrono::steady_clock::now();
+	auto lap = [&](const char* what) {
+		if (!trace) return;
+		const auto now = std::chrono::steady_clock::now();
+		std::fprintf(stderr, "[flatten] %-32s %9.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+		t_prev = now;
+	};
 	Flattener f(*flat);
 	f.walk(world, Xform());
+	lap("walk + bake + dedupe");
 	if (f.refs.empty()) throw std::runtime_error("flatten: the world holds no surface primitive");
 	std::vector<uint32_t> order;
 	if (opt.reference_tree) build_bvh_median(f.bounds, flat->nodes, order);
 	else build_bvh_sah(f.bounds, opt.max_leaf_size, flat->nodes, order);
+	lap("BVH build");
 	flat->prim_refs.resize(order.size());
 	for (size_t k = 0; k < order.size(); ++k) flat->prim_refs[k] = f.refs[order[k]];
 	perlin_permutation_table(0, flat->perlin_perm);  // Perlin::default(), texture.rs:104
 	flat->finish();
+	lap("finish");
 	return flat;
 }
 

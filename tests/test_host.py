@@ -2,6 +2,8 @@
 ranks primitives correctly (checked by a numpy brute force over the flattened arrays against the
 oracle's tree walk), and the SAH BVH is a valid tree.  No GPU needed."""
 import ctypes as C
+import os
+import sys
 import filecmp
 
 import numpy as np
@@ -239,6 +241,52 @@ def test_gsh_bvh_build_entry_point():
     assert sorted(order.tolist()) == list(range(n)) and 0 < nn.value <= 2 * n - 1
     leaves = sum(nodes[i].ref_count for i in range(nn.value))
     assert leaves == n
+
+
+def _bvh(bounds, threads):
+    """gsh_bvh_build with GSH_BUILD_THREADS set -> (nodes as python tuples, order)"""
+    n = bounds.shape[0]
+    nodes = (ffi.gs_bvh_node * (2 * n))()
+    order = np.empty(n, dtype=np.uint32)
+    nn = C.c_size_t()
+    old = os.environ.get("GSH_BUILD_THREADS")
+    os.environ["GSH_BUILD_THREADS"] = str(threads)
+    try:
+        ffi.check_host(ffi.host_lib().gsh_bvh_build(bounds.ctypes.data, n, 1, nodes, C.byref(nn), order.ctypes.data))
+    finally:
+        if old is None:
+            del os.environ["GSH_BUILD_THREADS"]
+        else:
+            os.environ["GSH_BUILD_THREADS"] = old
+    return [nodes[i] for i in range(nn.value)], order
+
+
+def _canonical(nodes, order, i=0):
+    """the tree as nested tuples, independent of how the nodes are numbered"""
+    nd = nodes[i]
+    box = (tuple(nd.bounds_min), tuple(nd.bounds_max))
+    if nd.ref_count > 0:
+        return (box, tuple(sorted(int(order[nd.first_ref + k]) for k in range(nd.ref_count))))
+    assert nd.left > i and nd.right > i   # gs_scene_create requires children after their parent
+    return (box, _canonical(nodes, order, nd.left), _canonical(nodes, order, nd.right))
+
+
+def test_threaded_bvh_build_gives_the_same_tree():
+    """subtrees built by several threads (scenes of >= 50 000 primitives; forced here on a small one): same splits, same
+    boxes, same leaves as the single-threaded build, and the same node array on every run"""
+    sys.setrecursionlimit(10000)
+    rng = np.random.default_rng(3)
+    n = 6000
+    c = rng.random((n, 3)) * np.array([40.0, 5.0, 20.0])
+    r = 0.05 + 0.4 * rng.random((n, 1))
+    b = np.ascontiguousarray(np.concatenate([c - r, c + r], 1), dtype=np.float64)
+    seq_nodes, seq_order = _bvh(b, 1)
+    par_nodes, par_order = _bvh(b, 4)
+    assert len(seq_nodes) == len(par_nodes) == 2 * n - 1
+    assert _canonical(seq_nodes, seq_order) == _canonical(par_nodes, par_order)
+    again_nodes, again_order = _bvh(b, 4)
+    assert np.array_equal(par_order, again_order)
+    assert all((a.left, a.right, a.first_ref, a.ref_count) == (x.left, x.right, x.first_ref, x.ref_count) for a, x in zip(par_nodes, again_nodes))
 
 
 def test_camera_abi_matches_the_oracle_camera():
