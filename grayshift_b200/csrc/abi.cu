@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/grayshift.h"
@@ -26,6 +27,22 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
 		cudaError_t e_ = (call);                                                                          \
 		if (e_ != cudaSuccess) return fail(GS_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
 	} while (0)
+
+// Independent iterations over the host threads (scene creation of a 10^6-primitive scene spends most of its time in
+// such loops); small ranges stay on the calling thread.
+template <class F> void parallel_for(size_t n, F&& body) {
+	unsigned threads = std::thread::hardware_concurrency();
+	threads = threads > 16u ? 16u : threads;
+	if (n < 65536 || threads < 2) { for (size_t i = 0; i < n; ++i) body(i); return; }
+	std::vector<std::thread> pool;
+	const size_t chunk = (n + threads - 1) / threads;
+	for (unsigned t = 0; t < threads; ++t) {
+		const size_t lo = (size_t)t * chunk, hi = lo + chunk < n ? lo + chunk : n;
+		if (lo >= hi) break;
+		pool.emplace_back([lo, hi, &body]() { for (size_t i = lo; i < hi; ++i) body(i); });
+	}
+	for (auto& th : pool) th.join();
+}
 
 float float_down(double x) { float f = (float)x; if ((double)f > x) f = std::nextafterf(f, -INFINITY); return f; }
 float float_up(double x) { float f = (float)x; if ((double)f < x) f = std::nextafterf(f, INFINITY); return f; }
@@ -387,7 +404,7 @@ int build_nodes(gs_scene* s, double origin_limit) {
 		for (int a = 0; a < 3; ++a) { mnmx[a * 2] = float_down(c.bounds_min[a] - pad); mnmx[a * 2 + 1] = float_up(c.bounds_max[a] + pad); }
 	};
 	auto link = [&](int abi) { return s->h_node_to_dnode[abi] >= 0 ? s->h_node_to_dnode[abi] : s->h_leaf_code[abi]; };
-	for (size_t k = 0; k < s->h_bfs.size(); ++k) {
+	parallel_for(s->h_bfs.size(), [&](size_t k) {
 		const gs_bvh_node& n = s->h_nodes[s->h_bfs[k]];
 		float b0[6], b1[6];
 		child_box(n.left, b0); child_box(n.right, b1);
@@ -397,7 +414,7 @@ int build_nodes(gs_scene* s, double origin_limit) {
 		d.z01 = make_float4(b0[4], b0[5], b1[4], b1[5]);
 		d.link = make_int4(link(n.left), link(n.right), 0, 0);
 		out[k] = d;
-	}
+	});
 	if (out.size() < (size_t)kNodePad) {  // also covers the single-leaf tree: the pointer stays valid
 		DNode d; std::memset(&d, 0, sizeof d);
 		out.resize(kNodePad, d);
@@ -530,6 +547,10 @@ int gs_scene_create(const gs_scene_desc* d, int device, gs_scene** out) {
 	std::vector<DTriangle> tris; std::vector<int2> tri_aux;
 	std::vector<DSphere> spheres; std::vector<double4> sph_path; std::vector<int2> sph_aux;
 	std::vector<DQuad> quads; std::vector<int2> quad_aux; std::vector<int> quad_order;
+	refs.reserve(d->n_prim_refs);
+	spheres.reserve(d->n_spheres); sph_path.reserve(d->n_spheres); sph_aux.reserve(d->n_spheres);
+	quads.reserve(d->n_quads); quad_aux.reserve(d->n_quads); quad_order.reserve(d->n_quads);
+	tris.reserve(d->n_triangles); tri_aux.reserve(d->n_triangles);
 	{
 		std::vector<int> stack{0};
 		while (!stack.empty()) {
