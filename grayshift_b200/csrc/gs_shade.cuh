@@ -354,13 +354,12 @@ __device__ __forceinline__ bool segment_begin(const DeviceScene& sc, const DCame
 		const Ray& ray = st.ray;
 		const double a = ray.dx * ray.dx + ray.dy * ray.dy + ray.dz * ray.dz;
 		const double inv_a = f64_rcp(a);
-		// media stream: counter word 3 = 1, block = bounce * 64 + group, 4 media per block.  (Drawing from the path's own
-		// stream instead saves one Philox block per level: measured +1 % on C4, not worth a second draw order.)
-		uint4 blk = make_uint4(0u, 0u, 0u, 0u);
+		// One draw per medium from the path's own Philox stream, in medium order, between the scatter draws of the previous
+		// level and those of this one (the reference draws inside ConstantMedium::hit, volume.rs:48, wherever its traversal
+		// happens to be; a free-flight draw is independent of everything else).  A separate stream for the media cost one
+		// more Philox block per level: a third of all Philox work on C4.
 		for (int mi = 0; mi < sc.n_media; ++mi) {
-			if ((mi & 3) == 0) blk = philox4x32_10(st.rng.pixel, st.rng.sample, st.bounce * 64u + (uint32_t)(mi >> 2), 1u, st.rng.k0, st.rng.k1);
-			uint32_t w = (mi & 3) == 0 ? blk.x : ((mi & 3) == 1 ? blk.y : ((mi & 3) == 2 ? blk.z : blk.w));
-			float u01 = (float)(w >> 8) * (1.0f / 16777216.0f);
+			const float u01 = st.rng.next_f32();
 			double tm;
 			if (medium_event(sc, sc.media[mi], ray, a, inv_a, 0.001, tmax, u01, tm)) { tmax = tm; medium_hit = mi; }
 		}

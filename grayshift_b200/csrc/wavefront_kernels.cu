@@ -97,16 +97,18 @@ __global__ void __launch_bounds__(kBlock) wf_traverse_kernel(const __grid_consta
 						if (P.sc.n_media > 0) {
 							const double a = ray.dx * ray.dx + ray.dy * ray.dy + ray.dz * ray.dz;
 							const double inv_a = f64_rcp(a);
-							const uint32_t bounce = id.w & 0xffffu;
-							uint4 blk = make_uint4(0u, 0u, 0u, 0u);
+							// the media draw from the path's own stream (same order as the megakernel's segment_begin); the
+							// advanced draw counter goes back into the pool for the shade kernel
+							PathRng rng;
+							rng.pixel = id.x; rng.sample = id.y; rng.draw = id.z;
+							rng.k0 = (uint32_t)P.seed; rng.k1 = (uint32_t)(P.seed >> 32);
+							if (id.z & 3u) rng.buf = philox4x32_10(id.x, id.y, id.z >> 2, 0u, rng.k0, rng.k1);
 							for (int mi = 0; mi < P.sc.n_media; ++mi) {
-								if ((mi & 3) == 0)
-									blk = philox4x32_10(id.x, id.y, bounce * 64u + (uint32_t)(mi >> 2), 1u, (uint32_t)P.seed, (uint32_t)(P.seed >> 32));
-								const uint32_t w = (mi & 3) == 0 ? blk.x : ((mi & 3) == 1 ? blk.y : ((mi & 3) == 2 ? blk.z : blk.w));
-								const float u01 = (float)(w >> 8) * (1.0f / 16777216.0f);
+								const float u01 = rng.next_f32();
 								double tm;
 								if (medium_event(P.sc, P.sc.media[mi], ray, a, inv_a, 0.001, tmax, u01, tm)) { tmax = tm; medium = mi; }
 							}
+							reinterpret_cast<uint32_t*>(P.pool.ids + s)[2] = rng.draw;
 						}
 						trav_init(P.sc, tv, stack, tmax);
 						rc = ray_consts(ray, tmax);
