@@ -4,6 +4,7 @@
 //! Usage from the reference's types (patch points, see rust/README.md):
 //!   impl Hittable for Sphere       { fn flatten(&self, xf: &Xform, out: &mut SceneBuilder) { out.push_sphere(xf, ...) } }
 //!   impl Hittable for Quad         { fn flatten(..) { out.push_quad(xf, self.q, self.u, self.v, &self.material) } }
+//!   impl Hittable for Triangle     { fn flatten(..) { out.push_triangle(xf, self.a, self.b, self.c, &self.material) } }
 //!   impl Hittable for HittableList { fn flatten(..) { for o in &self.objects { o.flatten(xf, out) } } }
 //!   impl Hittable for BVHNode      { fn flatten(..) { self.left.flatten(xf, out); if let Some(r) = &self.right { r.flatten(xf, out) } } }
 //!   impl Hittable for Translate    { fn flatten(..) { self.object.flatten(&xf.translated(self.offset), out) } }
@@ -55,6 +56,7 @@ pub enum ImagePixels {
 pub struct SceneBuilder {
     pub spheres: Vec<gs_sphere>,
     pub quads: Vec<gs_quad>,
+    pub triangles: Vec<gs_triangle>,
     pub boundary_spheres: Vec<gs_sphere>,
     pub boundary_quads: Vec<gs_quad>,
     pub media: Vec<gs_medium>,
@@ -158,6 +160,23 @@ impl SceneBuilder {
         self.quads.push(g);
     }
 
+    /// Triangle::new(a, b, c, material) (triangle.rs:20-31): the three vertices go through the instance transform.
+    pub fn push_triangle(&mut self, xf: &Xform, a: [f64; 3], b: [f64; 3], c: [f64; 3], material: i32) {
+        assert!(self.open_medium.is_none(), "a triangle cannot bound a ConstantMedium (not convex)");
+        let (a, b, c) = (xf.point(a), xf.point(b), xf.point(c));
+        let g = gs_triangle { a, b, c, material, prim_id: self.next_prim_id, order: self.next_order, reserved: 0 };
+        self.next_prim_id += 1;
+        self.next_order += 1;
+        let mut bb = [0.0; 6];
+        for k in 0..3 {
+            bb[k] = a[k].min(b[k]).min(c[k]);
+            bb[k + 3] = a[k].max(b[k]).max(c[k]);
+        }
+        self.bounds.push(bb);
+        self.refs.push((2u32 << 30) | (self.triangles.len() as u32));
+        self.triangles.push(g);
+    }
+
     /// ConstantMedium (volume.rs:10-28): its boundary primitives go to the boundary arrays.
     pub fn begin_medium(&mut self, xf: &Xform) {
         // the medium's fixed normal (1,0,0) (volume.rs:57) would be rotated by an enclosing RotateY
@@ -186,6 +205,7 @@ impl SceneBuilder {
         FlatScene {
             spheres: self.spheres,
             quads: self.quads,
+            triangles: self.triangles,
             boundary_spheres: self.boundary_spheres,
             boundary_quads: self.boundary_quads,
             media: self.media,
@@ -205,6 +225,7 @@ impl SceneBuilder {
 pub struct FlatScene {
     pub spheres: Vec<gs_sphere>,
     pub quads: Vec<gs_quad>,
+    pub triangles: Vec<gs_triangle>,
     pub boundary_spheres: Vec<gs_sphere>,
     pub boundary_quads: Vec<gs_quad>,
     pub media: Vec<gs_medium>,
@@ -252,8 +273,8 @@ impl FlatScene {
             images: self.image_descs.as_ptr(),
             n_images: self.image_descs.len(),
             perlin_perm: if self.has_noise { self.perlin_perm.as_ptr() } else { std::ptr::null() },
-            triangles: std::ptr::null(), // Triangle::flatten -> push_triangle: same pattern as push_quad (kind 2)
-            n_triangles: 0,
+            triangles: if self.triangles.is_empty() { std::ptr::null() } else { self.triangles.as_ptr() },
+            n_triangles: self.triangles.len(),
         }
     }
 }

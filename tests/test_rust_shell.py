@@ -84,3 +84,17 @@ def test_build_rs_compiles_the_same_translation_units_as_the_makefile():
     units = sorted(set(re.findall(r"(\w+\.cu)\b", mk)))
     assert units == sorted(set(re.findall(r'"(\w+\.cu)"', rs))), "build.rs and the Makefile list different .cu files"
     assert "compute_100a,code=sm_100a" in rs and "-fmad=false" in rs
+
+
+def test_rust_scene_builder_covers_every_primitive_kind_of_the_abi():
+    """the flattener twin pushes spheres, quads and triangles with the reference kinds 0 / 1 / 2 of GS_PRIM_REF and hands
+    every array of gs_scene_desc to the library"""
+    sb = open(os.path.join(ROOT, "rust", "src", "scene_builder.rs")).read()
+    for fn in ("push_sphere", "push_quad", "push_triangle", "begin_medium", "end_medium", "finish", "desc"):
+        assert re.search(rf"pub fn {fn}\b", sb), f"scene_builder.rs lacks {fn}"
+    assert "(1u32 << 30)" in sb and "(2u32 << 30)" in sb
+    desc_fields = [f for f, _ in ffi.gs_scene_desc._fields_]
+    body = sb[sb.index("gs_scene_desc {"):]
+    body = body[:body.index("}\n    }")]
+    for f in desc_fields:
+        assert re.search(rf"\b{f}:", body), f"FlatScene::desc() does not set gs_scene_desc.{f}"
