@@ -499,3 +499,16 @@ def test_adaptive_pixel_split_equals_the_single_gpu_render():
     assert torch.equal(merged[:, 3], whole[:, 3])
     assert 32 <= float(whole[:, 3].min()) and float(whole[:, 3].max()) <= 1024
     assert torch.allclose(merged[:, :3], whole[:, :3], rtol=1e-4, atol=1e-5)
+
+
+def test_more_than_2_32_work_items_in_one_launch():
+    """64-bit work-item indexing: config 2 at 4800 spp is 4.4e9 (pixel, sample) items in a single launch of the megakernel
+    (a fifth of a second on one B200); every pixel must end up with exactly its samples"""
+    dev = gs.DeviceScene(gs.HostScene.build("c2", spp=4800))
+    n_items = dev.width * dev.height * 4800
+    assert n_items > 1 << 32
+    rgb, counts, st = dev.render(seed=1)
+    assert st.paths == n_items and counts.min() == counts.max() == 4800
+    assert np.all(np.isfinite(rgb))
+    ref = gs.DeviceScene(gs.HostScene.build("c2", spp=64)).render(seed=2)[0]
+    assert abs(float(ref.mean()) - float(rgb.mean())) <= 0.02 * float(rgb.mean())
