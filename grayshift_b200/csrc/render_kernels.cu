@@ -14,6 +14,10 @@
 #include "gs_internal.h"
 #include "gs_kernel_util.cuh"
 
+// "variable st is used before its value is set": every lane starts in state kDead and reads its PathState only after
+// path_begin wrote it; zero-initialising it to please the front end changes ptxas's register allocation (+36 B of spills).
+#pragma nv_diag_suppress 549
+
 namespace gs {
 
 // Lane states of the megakernel.  A lane is a path; the warp alternates between two phases:
