@@ -4,7 +4,10 @@
 
 namespace gs {
 
-constexpr int kBlock = 128;
+#ifndef GS_BLOCK
+#define GS_BLOCK 128  // threads per CTA of the render kernels (a multiple of 32, at least 64)
+#endif
+constexpr int kBlock = GS_BLOCK;
 constexpr unsigned kFull = 0xffffffffu;
 
 // One 128-bit vector reduction into the (sum r, sum g, sum b, count) accumulator (sm_90+).
