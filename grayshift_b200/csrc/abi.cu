@@ -82,6 +82,9 @@ template <class T> struct DevBuf {
 	}
 	cudaError_t alloc(size_t count) {
 		if (count <= n && p) return cudaSuccess;
+		// growing a buffer a previous (asynchronous) render may still be using on a non-blocking stream: the pool's free
+		// is ordered on the legacy default stream only, so wait for the device first (rare path: the image got larger)
+		if (p) cudaDeviceSynchronize();
 		release();
 		n = count;
 		return dev_alloc(reinterpret_cast<void**>(&p), n * sizeof(T));
