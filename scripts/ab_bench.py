@@ -36,7 +36,7 @@ for cfg, width, spp in (("c4", 160, 16), ("c1", 160, 16), ("c3", 128, 16), ("c2"
     dev.close()
 if not ok:
     sys.exit(1)
-BENCH = {"scene3": (1200, 64), "scene5": (1200, 64), "scene9": (0, 0), "c4": (0, 64), "c1": (0, 1000), "c3": (0, 128), "c2": (0, 64), "c5": (1920, 8)}
+BENCH = {"scene7": (0, 64), "scene3": (1200, 64), "scene5": (1200, 64), "scene9": (0, 0), "c4": (0, 64), "c1": (0, 1000), "c3": (0, 128), "c2": (0, 64), "c5": (1920, 8)}
 line = f"{name:24s}"
 for cfg in cfgs:
     width, spp = BENCH[cfg]
