@@ -93,6 +93,7 @@ template <class T> struct DevBuf {
 };
 
 constexpr int kCounterSlots = 64;
+constexpr size_t kSmallSceneBytes = 128u << 10;     // C1 (486 spheres) is 47 KB, C3 2 KB, C4 (the one that wants the spill-free build) 490 KB
 constexpr unsigned kAdaptiveTailPixels = 2048;  // adaptive renders: below this many unfinished pixels, switch to one warp per pixel
 constexpr int kStatSlots = 16;  // [0..3] = gs_stats totals; [4..] only written by the GS_DIVERGENCE_STATS diagnostic build
 
@@ -147,6 +148,7 @@ struct gs_scene {
 	uint64_t launches = 0;
 	bool count_nodes = false;
 	bool has_triangles = false;  // selects the kernel variants that carry the triangle branch
+	bool small_scene = false;    // nodes + primitives fit the L1 with room to spare: the kernels built for one more CTA per SM
 	uint64_t h2d_bytes = 0;
 
 	// wavefront pipeline: path pool (structure of arrays) + counters.  Off by default: measured against the
@@ -706,6 +708,7 @@ int gs_scene_create(const gs_scene_desc* d, int device, gs_scene** out) {
 	ds.quads = s->quads.p; ds.quad_aux = s->quad_aux.p; ds.quad_order = s->quad_order.p;
 	ds.tris = s->tris.p; ds.tri_aux = s->tri_aux.p;
 	s->has_triangles = !tris.empty();
+	s->small_scene = d->n_nodes * sizeof(DNode) / 2 + spheres.size() * sizeof(DSphere) + quads.size() * sizeof(DQuad) + tris.size() * sizeof(DTriangle) <= kSmallSceneBytes;
 	ds.bnd_spheres = s->bnd_spheres.p; ds.bnd_sph_path = s->bnd_sph_path.p; ds.bnd_quads = s->bnd_quads.p;
 	ds.media = s->media.p; ds.materials = s->materials.p; ds.textures = s->textures.p; ds.images = s->images.p;
 	ds.perlin_perm = s->perm.p; ds.n_media = (int)d->n_media;
@@ -788,6 +791,7 @@ int gs_render_accumulate(gs_scene* s, const gs_camera* camera, uint64_t seed, ui
 	p.work_counter = next_counter(s);
 	p.stats = s->stats.p;
 	p.pixel_list = nullptr; p.n_list = nullptr; p.lum = nullptr;  // every pixel, no luminance statistics
+	p.small_scene = s->small_scene;
 	GS_CUDA(cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned long long), st));
 	GS_CUDA(launch_render_fixed(p, s->sm_count, s->count_nodes, s->has_triangles, st));
 	s->launches += 1;
@@ -834,6 +838,7 @@ int gs_render_adaptive_accumulate(gs_scene* s, const gs_camera* camera, const gs
 	p.accum = static_cast<float4*>(d_accum);
 	p.stats = s->stats.p;
 	p.lum = s->lum.p;
+	p.small_scene = s->small_scene;
 	for (unsigned long long r = 0; r < rounds; ++r) {
 		const int cur = (int)(r & 1ull), nxt = cur ^ 1;
 		if ((unsigned long long)settings->batch_size * (r + 1ull) > 0xffffffffull) return fail(GS_ERR_UNSUPPORTED, "sample index beyond 32 bits");

@@ -19,6 +19,7 @@ struct RenderParams {
 	const uint32_t* pixel_list;            // work item i belongs to pixel_list[i / sample_count]; nullptr = every pixel
 	const unsigned* n_list;                // device-resident length of pixel_list (total_items is derived from it on the device)
 	double2* lum;                          // per pixel (sum of luminance, sum of its square), camera.rs:132-133,146-147
+	bool small_scene;                      // nodes + primitives <= kSmallSceneBytes: the launch takes the 6-CTAs-per-SM build
 };
 
 struct AdaptiveParams {  // the stop test of camera.rs:150-164

@@ -38,7 +38,8 @@ enum LaneState : int { kDead = 0, kTraverse = 1, kShade = 2, kSetup = 3 };
                           // bound, so occupancy pays until spills eat the L1: 5 = 96 registers, 20 warps/SM, no spills -> best on
                           // C4 (1518 M paths/s; its 0.5 MB scene is the one that does not fit the L1); 6 = 80 registers with 256 B
                           // of spills in the shading code -> 1446 on C4 but +5 % on C1 and +7 % on C3 (small scenes); 4 = 110
-                          // registers -> 1403.  profiles/r01_v5_variant_sweeps.log
+                          // registers -> 1403.  profiles/r01_v5_variant_sweeps.log.  Scenes of <= 128 KB get the build with one
+                          // more CTA per SM (kernel variants with bit 3 set).
 #endif
 #ifndef GS_TOP_SMEM
 #define GS_TOP_SMEM 0     // nodes of the top BVH levels (breadth-first prefix) staged in shared memory per CTA; 0 = off.  Measured -9 %
@@ -54,8 +55,10 @@ constexpr int kBail = GS_BAIL;
 
 // kF: bit 0 = count BVH node visits, bit 1 = the scene holds triangles, bit 2 = one batch of the adaptive sampler (work items
 // come from a device-resident list of the pixels still sampling, and the luminance sums of camera.rs:146-147 are kept)
+// bit 3 = the scene's nodes and primitives fit the L1 several times over: one more CTA per SM (80 registers, some spills into the
+// shading code) -- measured +3...4 % on C1 / C3 and -3 % on C4, whose 0.5 MB working set feels the spills in the L1
 template <int kF>
-__global__ void __launch_bounds__(kBlock, GS_MIN_BLOCKS) render_fixed_kernel(const __grid_constant__ RenderParams P) {
+__global__ void __launch_bounds__(kBlock, (kF & 8) ? GS_MIN_BLOCKS + 1 : GS_MIN_BLOCKS) render_fixed_kernel(const __grid_constant__ RenderParams P) {
 	constexpr bool kAdaptive = (kF & 4) != 0;
 	const unsigned long long total_items = kAdaptive ? (unsigned long long)__ldg(P.n_list) * P.sample_count : P.total_items;
 	__shared__ uint8_t s_perm[256];
@@ -415,10 +418,12 @@ __global__ void __launch_bounds__(kBlock) path_radiance_kernel(const __grid_cons
 template <int kF>
 static void fixed_occupancy(int* n) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(n, render_fixed_kernel<kF>, kBlock, 0); }
 
-// kernel variant: bit 0 = count node visits, bit 1 = triangles, bit 2 = adaptive batch (never combined with bit 0)
+// kernel variant: bit 0 = count node visits, bit 1 = triangles, bit 2 = adaptive batch (never combined with bit 0),
+// bit 3 = small scene (never combined with bit 0)
 static int fixed_variant(const RenderParams& p, bool count_nodes, bool triangles) {
-	if (p.pixel_list) return 4 | (triangles ? 2 : 0);
-	return (count_nodes ? 1 : 0) | (triangles ? 2 : 0);
+	if (p.pixel_list) return 4 | (triangles ? 2 : 0) | (p.small_scene ? 8 : 0);
+	if (count_nodes) return 1 | (triangles ? 2 : 0);
+	return (triangles ? 2 : 0) | (p.small_scene ? 8 : 0);
 }
 
 static int fixed_blocks_per_sm(int variant) {
@@ -429,7 +434,11 @@ static int fixed_blocks_per_sm(int variant) {
 		case 2: fixed_occupancy<2>(&n); break;
 		case 3: fixed_occupancy<3>(&n); break;
 		case 4: fixed_occupancy<4>(&n); break;
-		default: fixed_occupancy<6>(&n); break;
+		case 6: fixed_occupancy<6>(&n); break;
+		case 8: fixed_occupancy<8>(&n); break;
+		case 10: fixed_occupancy<10>(&n); break;
+		case 12: fixed_occupancy<12>(&n); break;
+		default: fixed_occupancy<14>(&n); break;
 	}
 	return n > 0 ? n : 1;
 }
@@ -449,7 +458,11 @@ cudaError_t launch_render_fixed(const RenderParams& p, int sm_count, bool count_
 		case 2: render_fixed_kernel<2><<<(unsigned)grid, kBlock, 0, stream>>>(p); break;
 		case 3: render_fixed_kernel<3><<<(unsigned)grid, kBlock, 0, stream>>>(p); break;
 		case 4: render_fixed_kernel<4><<<(unsigned)grid, kBlock, 0, stream>>>(p); break;
-		default: render_fixed_kernel<6><<<(unsigned)grid, kBlock, 0, stream>>>(p); break;
+		case 6: render_fixed_kernel<6><<<(unsigned)grid, kBlock, 0, stream>>>(p); break;
+		case 8: render_fixed_kernel<8><<<(unsigned)grid, kBlock, 0, stream>>>(p); break;
+		case 10: render_fixed_kernel<10><<<(unsigned)grid, kBlock, 0, stream>>>(p); break;
+		case 12: render_fixed_kernel<12><<<(unsigned)grid, kBlock, 0, stream>>>(p); break;
+		default: render_fixed_kernel<14><<<(unsigned)grid, kBlock, 0, stream>>>(p); break;
 	}
 	return cudaGetLastError();
 }
