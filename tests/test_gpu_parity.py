@@ -536,3 +536,25 @@ def test_random_scene_graph_image_within_the_noise_floor(tmp_path, seed):
     # the same streams on both sides: most pixels of the same-seed render agree closely
     same = ora.render(seed=1, rng=orc.OracleScene.PHILOX)[0]
     assert np.isclose(g, same, rtol=2e-2, atol=2e-3).all(axis=2).mean() > 0.9
+
+
+def test_render_on_a_side_stream_matches_the_default_stream():
+    """gs_render_accumulate takes the caller's stream (torch side streams are non-blocking): scene arrays come from the
+    stream-ordered pool on the default stream, the work counter reset and the kernel are ordered on the caller's stream"""
+    import torch
+
+    host = gs.HostScene.build("c4", width=96, spp=8)
+    dev = gs.DeviceScene(host)
+    n = dev.width * dev.height
+    a = torch.zeros((n, 4), device="cuda")
+    dev.render_accumulate(a.data_ptr(), seed=9, sample_begin=0, sample_count=8)
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    b = torch.zeros((n, 4), device="cuda")
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for k in range(4):   # four launches back to back on the side stream, two samples each
+            dev.render_accumulate(b.data_ptr(), seed=9, sample_begin=2 * k, sample_count=2, stream=side.cuda_stream)
+    side.synchronize()
+    assert torch.equal(a[:, 3], b[:, 3]) and float(a[:, 3].min()) == 8.0
+    assert torch.allclose(a[:, :3], b[:, :3], rtol=1e-4, atol=1e-5)
