@@ -147,14 +147,21 @@ class DeviceScene:
         ffi.check(self._lib.gs_stats_read(self._h, C.byref(st)))
         return st
 
-    def trace_closest(self, rays, tmin=0.001, tmax=1.7976931348623157e308):
-        """Hittable::hit over the surface primitives: rays [n,7] f64 -> (prim_id int32 [n], t f64 [n])."""
+    def trace_closest(self, rays, tmin=0.001, tmax=1.7976931348623157e308, fast=False):
+        """Hittable::hit over the surface primitives: rays [n,7] f64 -> (prim_id int32 [n], t f64 [n]).
+        fast=True: answered by the render kernels' build of the traversal (FMA contraction, approximate f64 division)."""
         rays = np.ascontiguousarray(rays, dtype=np.float64)
         n = rays.shape[0]
         ids = np.empty(n, dtype=np.int32)
         t = np.empty(n, dtype=np.float64)
-        ffi.check(self._lib.gs_trace_closest(self._h, rays.ctypes.data, n, tmin, tmax, ids.ctypes.data, t.ctypes.data))
+        fn = self._lib.gs_trace_closest_fast if fast else self._lib.gs_trace_closest
+        ffi.check(fn(self._h, rays.ctypes.data, n, tmin, tmax, ids.ctypes.data, t.ctypes.data))
         return ids, t
+
+    def info(self, key):
+        v = C.c_int64()
+        ffi.check(self._lib.gs_scene_get_info(self._h, key.encode(), C.byref(v)))
+        return v.value
 
     def camera_rays(self, seed, sample, pixel_begin=0, pixel_end=None):
         pixel_end = self.width * self.height if pixel_end is None else pixel_end

@@ -4,9 +4,14 @@
 //
 // Layout in HBM (all immutable after gs_scene_create; C1-C4 working sets are L1/L2 resident,
 // C5 ~100 MB fits the 126 MB L2):
-//   nodes     DNode[ ]     64 B, two child boxes per node (fp32, padded outward), 4 x 128-bit loads
+//   nodes     DNode[ ]     64 B, two child boxes per node (fp32, padded outward), 4 x 128-bit loads   (binary tree: scenes
+//                          whose nodes live in the L1)
+//   nodes8    DNode8[ ]    96 B, eight children per node, boxes as 8-bit offsets on a power-of-two grid from the node's
+//                          corner, children in octant order; 5 x 128-bit loads per visit (6th chunk only for quad /
+//                          triangle leaves)                                                        (large scenes)
 //   refs      uint32[ ]    leaf -> primitive references, kind<<30 | index, leaf order
-//   spheres   DSphere[ ]   32 B f64 (cx,cy,cz,r; r<0 flags a moving sphere), leaf order, 2 x 128-bit loads
+//   spheres   DSphere[ ]   32 B f64 (cx,cy,cz,r; r keeps the sign the caller gave it, sphere.rs:91), leaf order, 2 x 128-bit
+//                          loads; a MOVING sphere is flagged by reference kind 3 (same array)
 //   sph_path  double4[ ]   only read for moving spheres
 //   quads     DQuad[ ]     96 B f64 (plane n,d; barycentric functionals A,qa,B,qb), 6 x 128-bit loads
 //   *_aux     int2[ ]      (material, prim_id) per primitive, read once per accepted hit
@@ -19,10 +24,6 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#ifndef GS_WIDE
-#define GS_WIDE 0  // 1 = four-wide tree with quantised child boxes (DNode4) instead of the binary tree (DNode)
-#endif
-
 namespace gs {
 
 // ------------------------------------------------------------------------------------------
@@ -34,33 +35,42 @@ struct __align__(16) DNode {
 	float4 z01;  // c0.min.z, c0.max.z, c1.min.z, c1.max.z
 	int4 link;   // child0, child1 (>= 0 internal node index; < 0 leaf code), unused, unused
 };
-// Wide node (GS_WIDE builds): four children in 64 bytes.  The children's boxes are stored as 8-bit offsets on a
-// power-of-two grid anchored at the node's own lower corner (conservative: lower planes rounded down, upper planes up),
-// so a node costs as many bytes as a binary one but replaces two levels: half the dependent fetches and half the bytes
-// per ray.  Matters when the tree does not fit the L1 (config 5: 10^6 spheres, node fetches come from L2).
-struct __align__(16) DNode4 {
-	float ox, oy, oz;   // lower corner of the node's box (fp32, already padded outward)
-	uint32_t exps;      // byte a = biased fp32 exponent of the grid step of axis a (step = 2^(e - 127))
-	uint32_t qlox, qhix, qloy, qhiy;   // byte i = child i: lower / upper plane in grid steps from the corner
-	uint32_t qloz, qhiz;
-	int pad0, pad1;
-	int4 link;          // child i: > 0 node index, < 0 leaf code, 0 = no child (node 0 is the root, never a child)
+// Eight-wide compressed node (large scenes: config 5's 10^6 spheres, whose binary nodes come from L2).  96 bytes:
+//   chunk 0   lower corner of the node's box (fp32, padded outward), biased fp32 exponents of the grid step per axis, imask
+//   chunk 1-3 per axis: the children's lower planes (slots 0-3, 4-7) and upper planes (slots 0-3, 4-7) in grid steps from
+//             the corner, one byte each (lower planes rounded down, upper planes up: conservative); an empty slot holds
+//             lower = 255 > upper = 0 and is never hit
+//   chunk 4   meta byte per slot (leaf children: kind << 6 | offset into that kind's run of primitives; kind 3 = the leaf
+//             code sits in leaf_links8[node * 8 + slot]: leaves of several primitives, moving spheres), child_base (internal
+//             child in slot k is node child_base + popc(imask & ((1 << k) - 1))), sphere_base
+//   chunk 5   quad_base, tri_base (read only when such a leaf is intersected)
+// Children are assigned to slots by the octant of their centre relative to the node's, so that visiting the hit slots
+// in the order of (slot XOR ray octant) is near-to-far without a sort (Ylitie, Karras, Laine 2017); a visit costs one
+// dependent fetch where the binary tree needs three, and the traversal stack holds (node group, hit mask) pairs: at most
+// one entry per level of a tree a third as deep.
+struct __align__(16) DNode8 {
+	float px, py, pz;
+	uint32_t exps_imask;   // byte a = biased exponent of axis a's grid step (step = 2^(e - 127)), byte 3 = imask
+	uint32_t qx[4];        // lo[0..3], lo[4..7], hi[0..3], hi[4..7]
+	uint32_t qy[4];
+	uint32_t qz[4];
+	uint32_t meta[2];
+	uint32_t child_base;
+	uint32_t sphere_base;
+	uint32_t quad_base, tri_base, pad0, pad1;
 };
+constexpr int kMaxStack8 = 40;  // (node group, hits) entries; gs_scene_create checks the tree against it
 // leaf code: -1 - ((first_ref << 4) | count), 1 <= count <= 15; count == 0 marks a single-primitive leaf whose
 // reference (kind << 25 | index) sits in the first_ref field itself
 __host__ __device__ inline int leaf_code(uint32_t first, uint32_t count) { return -1 - (int)((first << 4) | count); }
 // Negative (so the inner "internal node" loop stops on it) and not a valid leaf code: it would need
 // first_ref = 2^27 - 1 with count 15, which gs_scene_create rejects.
 constexpr int kStackSentinel = -2147483647 - 1;
-#if GS_WIDE
-constexpr int kMaxStack = 96;  // a wide node pushes up to three siblings
-#else
 constexpr int kMaxStack = 64;
-#endif
 constexpr int kNodePad = 512;  // the device node array holds at least this many entries (zero boxes beyond the tree), so a
                                // kernel may stage a fixed-size breadth-first prefix in shared memory without a bounds check
 
-struct __align__(16) DSphere { double cx, cy, cz, r; };  // r < 0: moving, |r| is the radius
+struct __align__(16) DSphere { double cx, cy, cz, r; };  // r is signed as given (a negative radius flips the normal, sphere.rs:91)
 struct __align__(16) DQuad {
 	double nx, ny, nz, d;    // unit plane normal and offset (quad.rs:32-36, plane.rs:15-18)
 	double ax, ay, az, qa;   // alpha = P.A - qa with A = v x w    (== w . (planar x v), quad.rs:88)
@@ -74,18 +84,22 @@ struct __align__(16) DTriangle {
 struct __align__(16) DMaterial { int kind; int tex; float ar, ag, ab; float param; int pad0, pad1; };
 struct __align__(16) DTexture { int kind; int a; int b; float scale; float cr, cg, cb; float pad; double scale_inv_d; double scale_d; };
 struct DImage { int w, h; int format; int pad; const void* texels; };  // uchar4 (u8) or float4 (f32) texels, row 0 = top
-struct DMedium { int sph_first, sph_count, quad_first, quad_count; double neg_inv_density; int phase_mat; int index; };
+struct DMedium { int sph_first, sph_count, quad_first, quad_count; double neg_inv_density; int phase_mat; int flags; };  // flags bit 0: the single boundary sphere moves
 
 constexpr uint32_t kRefKindShift = 30;
 constexpr uint32_t kRefIndexMask = (1u << 30) - 1u;
+// reference kinds on the device: 0 sphere, 1 quad, 2 triangle (= GS_PRIM_*), 3 = a MOVING sphere (index into `spheres`)
+constexpr uint32_t kKindSphere = 0u, kKindQuad = 1u, kKindTriangle = 2u, kKindMovingSphere = 3u;
 
 struct DeviceScene {
 	const DNode* nodes;
-	const DNode4* nodes4;  // GS_WIDE builds: the wide tree (then `nodes` is null)
+	const DNode8* nodes8;       // the eight-wide tree (kernels with the wide traversal); either array may be null
+	const int* leaf_links8;     // nodes8: leaf code of slot k of node n at [n * 8 + k] where the meta byte says kind 3
 	const uint32_t* refs;
 	const DSphere* spheres;
 	const double4* sph_path;
 	const int2* sph_aux;
+	const float2* sph_uvrot;    // (cos, sin) of the RotateY an instance was baked with: sphere_uv works on the OBJECT-space normal
 	const DQuad* quads;
 	const int2* quad_aux;
 	const int* quad_order;  // reference visiting rank, read only on exact-t ties
@@ -213,13 +227,13 @@ __device__ __forceinline__ double f64_sqrt(double v) {
 // the two roots (h -+ sqrt(disc)) / a become multiplications by 1/a (one f64 division per ray instead of up to
 // two per candidate; differs from the reference's quotient by at most 1 ulp).  Strict interval (surrounds,
 // interval.rs:33-35).
-__device__ __forceinline__ bool hit_sphere(const DSphere& s, const double4* __restrict__ path, uint32_t index, const Ray& r, double a,
-                                           double inv_a, double tmin, double tmax, double& t_out) {
-	double cx = s.cx, cy = s.cy, cz = s.cz, rad = s.r;
-	if (rad < 0.0) {  // moving: center_start + time * center_path (sphere.rs:51-53)
+__device__ __forceinline__ bool hit_sphere(const DSphere& s, const double4* __restrict__ path, uint32_t index, bool moving, const Ray& r,
+                                           double a, double inv_a, double tmin, double tmax, double& t_out) {
+	double cx = s.cx, cy = s.cy, cz = s.cz;
+	const double rad = s.r;  // enters only squared here; its sign matters for the normal (sphere.rs:91)
+	if (moving) {  // center_start + time * center_path (sphere.rs:51-53)
 		double4 p = path[index];
 		cx = cx + r.time * p.x; cy = cy + r.time * p.y; cz = cz + r.time * p.z;
-		rad = -rad;
 	}
 	double ocx = cx - r.ox, ocy = cy - r.oy, ocz = cz - r.oz;
 	double h = r.dx * ocx + r.dy * ocy + r.dz * ocz;
@@ -308,11 +322,6 @@ __device__ __forceinline__ float safe_rcp(float d) {
 #ifndef GS_NODE_LOAD
 #define GS_NODE_LOAD 1  // tuning knob: 1 = branch-free child selection (the link load is issued together with the box loads)
 #endif
-struct TravState {
-	int node;   // current node index / leaf code, kStackSentinel when the ray is finished
-	int sp;     // stack entries in use
-	Hit best;
-};
 
 struct RayConsts {  // per-ray values derived from the Ray; recomputed whenever a traversal is (re)entered
 	float idx, idy, idz;     // 1 / direction
@@ -330,117 +339,6 @@ __device__ __forceinline__ RayConsts ray_consts(const Ray& r, double t_closest) 
 	return c;
 }
 
-__device__ __forceinline__ void trav_init(const DeviceScene& sc, TravState& tv, int* stack, double tmax) {
-	stack[0] = kStackSentinel;
-	tv.sp = 1;
-	tv.node = sc.root;
-	tv.best.t = tmax; tv.best.ref = kNoHit; tv.best.u = 0.f; tv.best.v = 0.f;
-}
-
-// The arithmetic of one node step (see node_step).
-template <bool kCount>
-__device__ __forceinline__ void node_test(const float4 xy0, const float4 xy1, const float4 z01, int link0, int link1, const RayConsts& rc,
-                                          TravState& tv, int* stack, uint32_t* node_visits) {
-	if (kCount) ++(*node_visits);
-	float t0 = fmaf(xy0.x, rc.idx, -rc.oix), t1 = fmaf(xy0.y, rc.idx, -rc.oix);
-	float t2 = fmaf(xy0.z, rc.idy, -rc.oiy), t3 = fmaf(xy0.w, rc.idy, -rc.oiy);
-	float t4 = fmaf(z01.x, rc.idz, -rc.oiz), t5 = fmaf(z01.y, rc.idz, -rc.oiz);
-	const float en0 = fmaxf(fmaxf(fminf(t0, t1), fminf(t2, t3)), fmaxf(fminf(t4, t5), 0.0f));
-	const float ex0 = fminf(fminf(fmaxf(t0, t1), fmaxf(t2, t3)), fminf(fmaxf(t4, t5), rc.tmax32));
-	t0 = fmaf(xy1.x, rc.idx, -rc.oix); t1 = fmaf(xy1.y, rc.idx, -rc.oix);
-	t2 = fmaf(xy1.z, rc.idy, -rc.oiy); t3 = fmaf(xy1.w, rc.idy, -rc.oiy);
-	t4 = fmaf(z01.z, rc.idz, -rc.oiz); t5 = fmaf(z01.w, rc.idz, -rc.oiz);
-	const float en1 = fmaxf(fmaxf(fminf(t0, t1), fminf(t2, t3)), fmaxf(fminf(t4, t5), 0.0f));
-	const float ex1 = fminf(fminf(fmaxf(t0, t1), fmaxf(t2, t3)), fminf(fmaxf(t4, t5), rc.tmax32));
-	const bool h0 = en0 <= ex0, h1 = en1 <= ex1;
-#if GS_NODE_LOAD == 1
-	// Select form: both links are consumed unconditionally, so their load is issued with the box loads.  (In the
-	// branchy form below the compiler sinks the link load under the "some child hit" branch and every descent pays two
-	// dependent L1 round trips.)
-	const bool first0 = h0 && (!h1 || !(en1 < en0));
-	const int first = first0 ? link0 : link1, second = first0 ? link1 : link0;
-	if (h0 && h1) stack[tv.sp++] = second;
-	if (h0 || h1) tv.node = first;
-	else tv.node = stack[--tv.sp];
-#else
-	if (!h0 && !h1) { tv.node = stack[--tv.sp]; }
-	else {
-		int near = link0, far = link1;
-		if (h0 && h1) {
-			if (en1 < en0) { int tmp = near; near = far; far = tmp; }
-			stack[tv.sp++] = far;
-			tv.node = near;
-		} else tv.node = h0 ? near : far;
-	}
-#endif
-}
-
-// One wide node (GS_WIDE): the four children's slabs from the quantised planes, t = q * (step / d) + (corner - o) / d
-// -- one FMA per plane after three multiplications and three FMAs per node -- with the near / far plane of each axis picked
-// by the sign of the direction (word select per node instead of a min and a max per child and axis).  The hit children
-// are sorted by entry distance with a five-exchange network; the nearest is visited next, the others are pushed
-// far-to-near.  Precondition: tv.node >= 0.
-__device__ __forceinline__ float q8(uint32_t w, int i) { return (float)((w >> (8 * i)) & 0xffu); }
-
-template <bool kCount>
-__device__ __forceinline__ void node_step4(const DeviceScene& sc, const RayConsts& rc, TravState& tv, int* stack, uint32_t* node_visits) {
-	const uint4* np = reinterpret_cast<const uint4*>(sc.nodes4 + tv.node);
-	const uint4 hd = __ldg(np), qa = __ldg(np + 1);
-	const uint2 qb = __ldg(reinterpret_cast<const uint2*>(np + 2));
-	const int4 link = __ldg(reinterpret_cast<const int4*>(np + 3));
-	if (kCount) ++(*node_visits);
-	const float ax = __uint_as_float((hd.w & 0xffu) << 23) * rc.idx, bx = fmaf(__uint_as_float(hd.x), rc.idx, -rc.oix);
-	const float ay = __uint_as_float(((hd.w >> 8) & 0xffu) << 23) * rc.idy, by = fmaf(__uint_as_float(hd.y), rc.idy, -rc.oiy);
-	const float az = __uint_as_float(((hd.w >> 16) & 0xffu) << 23) * rc.idz, bz = fmaf(__uint_as_float(hd.z), rc.idz, -rc.oiz);
-	const uint32_t nx = rc.idx < 0.0f ? qa.y : qa.x, fx = rc.idx < 0.0f ? qa.x : qa.y;  // near / far planes
-	const uint32_t ny = rc.idy < 0.0f ? qa.w : qa.z, fy = rc.idy < 0.0f ? qa.z : qa.w;
-	const uint32_t nz = rc.idz < 0.0f ? qb.y : qb.x, fz = rc.idz < 0.0f ? qb.x : qb.y;
-	const int lk[4] = {link.x, link.y, link.z, link.w};
-	float key[4];
-#pragma unroll
-	for (int i = 0; i < 4; ++i) {
-		const float en = fmaxf(fmaxf(fmaf(q8(nx, i), ax, bx), fmaf(q8(ny, i), ay, by)), fmaxf(fmaf(q8(nz, i), az, bz), 0.0f));
-		const float ex = fminf(fminf(fmaf(q8(fx, i), ax, bx), fmaf(q8(fy, i), ay, by)), fminf(fmaf(q8(fz, i), az, bz), rc.tmax32));
-		key[i] = (en <= ex && lk[i] != 0) ? en : __int_as_float(0x7f800000);  // +inf = not hit
-	}
-	int l0 = lk[0], l1 = lk[1], l2 = lk[2], l3 = lk[3];
-	float k0 = key[0], k1 = key[1], k2 = key[2], k3 = key[3];
-#define GS_CSWAP(ka, la, kb, lb) { const bool sw = kb < ka; const float tk = sw ? kb : ka; const int tl = sw ? lb : la; kb = sw ? ka : kb; lb = sw ? la : lb; ka = tk; la = tl; }
-	GS_CSWAP(k0, l0, k1, l1) GS_CSWAP(k2, l2, k3, l3) GS_CSWAP(k0, l0, k2, l2) GS_CSWAP(k1, l1, k3, l3) GS_CSWAP(k1, l1, k2, l2)
-#undef GS_CSWAP
-	const float inf = __int_as_float(0x7f800000);
-	if (k3 < inf) stack[tv.sp++] = l3;
-	if (k2 < inf) stack[tv.sp++] = l2;
-	if (k1 < inf) stack[tv.sp++] = l1;
-	if (k0 < inf) tv.node = l0;
-	else tv.node = stack[--tv.sp];
-}
-
-// One internal node: AABB::hit (AABB.rs:58-113) for both children at once, near child first, far child pushed.
-// Slab distances in fp32 as fma(plane, 1/d, -o/d) against boxes padded by 8 ulp of the origin range
-// (abi.cu build_nodes): conservative, never culls a true hit.  Precondition: tv.node >= 0.
-// kTop > 0: the first kTop nodes (breadth-first order = the top levels of the tree) are read from the CTA's
-// shared-memory copy `top`; one generic-address load serves both cases, so lanes do not diverge on it.
-template <bool kCount, int kTop = 0>
-__device__ __forceinline__ void node_step(const DeviceScene& sc, const RayConsts& rc, TravState& tv, int* stack, uint32_t* node_visits,
-                                          const float4* top = nullptr) {
-#if GS_WIDE
-	node_step4<kCount>(sc, rc, tv, stack, node_visits);
-	return;
-#endif
-	const float4* np = reinterpret_cast<const float4*>(sc.nodes + tv.node);
-	if (kTop > 0) {
-		if (tv.node < kTop) np = top + tv.node * 4;
-		const float4 xy0 = np[0], xy1 = np[1], z01 = np[2];
-		const int2 link = *reinterpret_cast<const int2*>(np + 3);
-		node_test<kCount>(xy0, xy1, z01, link.x, link.y, rc, tv, stack, node_visits);
-		return;
-	}
-	const float4 xy0 = __ldg(np), xy1 = __ldg(np + 1), z01 = __ldg(np + 2);
-	const int4 link = __ldg(reinterpret_cast<const int4*>(np + 3));
-	node_test<kCount>(xy0, xy1, z01, link.x, link.y, rc, tv, stack, node_visits);
-}
-
 // One leaf: HittableList::hit over its primitives (hittable.rs:70-86) with the reference's interval rules.
 // `leaf` is a leaf code.  kTris = the scene holds triangles (kernels for scenes without any are
 // instantiated without the triangle branch: it costs registers and instruction-cache space in the hot loop).
@@ -456,59 +354,267 @@ __device__ __forceinline__ void leaf_intersect(const DeviceScene& sc, const Ray&
 		const uint32_t ref = direct ? (((first >> 25) << kRefKindShift) | (first & ((1u << 25) - 1u))) : __ldg(sc.refs + first + k);
 		const uint32_t index = ref & kRefIndexMask;
 		const uint32_t kind = ref >> kRefKindShift;
-		if (kTris && kind == 2u) {
+		if (kTris && kind == kKindTriangle) {
 			const DTriangle tr = load_triangle(sc.tris, index);
 			double t, u, v;
 			if (hit_triangle(tr, r, tmin, best.t, t, u, v)) { best.t = t; best.ref = ref; best.u = (float)u; best.v = (float)v; }
-		} else if (kind == 0u) {
-			const DSphere s = load_sphere(sc.spheres, index);
-			// |d|^2 (Vec3::length_squared, sphere.rs:71) and its reciprocal are recomputed per test: eleven f64
-			// instructions, against four registers held through the whole traversal of a register-bound kernel
-			const double a = r.dx * r.dx + r.dy * r.dy + r.dz * r.dz, inv_a = f64_rcp(a);
-			double t;
-			if (hit_sphere(s, sc.sph_path, index, r, a, inv_a, tmin, best.t, t)) { best.t = t; best.ref = ref; }
-		} else {
+		} else if (kind == kKindQuad) {
 			const DQuad q = load_quad(sc.quads, index);
 			double t, al, be;
 			if (hit_quad(q, r, tmin, best.t, t, al, be)) {
 				// exact tie between two quads: the one the reference visits later wins (t <= closest, plane.rs:27)
 				bool accept = true;
-				if (t == best.t && best.ref != kNoHit && (best.ref >> kRefKindShift) == 1u)
+				if (t == best.t && best.ref != kNoHit && (best.ref >> kRefKindShift) == kKindQuad)
 					accept = __ldg(sc.quad_order + index) > __ldg(sc.quad_order + (best.ref & kRefIndexMask));
 				// (alpha, beta) are the quad's texture coordinates (quad.rs:101-102); the render kernels recompute them from
 				// the hit point when an image texture asks for them instead of carrying two registers through the traversal
 				if (accept) { best.t = t; best.ref = ref; }
 			}
+		} else {  // sphere, stationary (kind 0) or moving (kind 3)
+			const DSphere s = load_sphere(sc.spheres, index);
+			// |d|^2 (Vec3::length_squared, sphere.rs:71) and its reciprocal are recomputed per test: eleven f64
+			// instructions, against four registers held through the whole traversal of a register-bound kernel
+			const double a = r.dx * r.dx + r.dy * r.dy + r.dz * r.dz, inv_a = f64_rcp(a);
+			double t;
+			if (hit_sphere(s, sc.sph_path, index, kind == kKindMovingSphere, r, a, inv_a, tmin, best.t, t)) { best.t = t; best.ref = ref; }
 		}
 	}
 	if (best.ref != kNoHit) rc.tmax32 = __double2float_ru(best.t);
 }
 
-// The leaf under tv.node, then pop.  Precondition: tv.node is a leaf code.
-template <bool kTris>
-__device__ __forceinline__ void leaf_step(const DeviceScene& sc, const Ray& r, RayConsts& rc, double tmin, TravState& tv, int* stack) {
-	leaf_intersect<kTris>(sc, r, rc, tmin, tv.best, tv.node);
-	tv.node = stack[--tv.sp];
-}
+// ==========================================================================================
+// Traversal policy 1: the binary tree (DNode).  State = (node, sp) + the per-thread stack of links.
+// ==========================================================================================
+struct Trav2 {
+	static constexpr int kStackWords = kMaxStack;
+	int node;   // current node index / leaf code, kStackSentinel when the ray is finished
+	int sp;     // stack entries in use
+	Hit best;
 
+	__device__ __forceinline__ void init(const DeviceScene& sc, const Ray&, int* stack, double tmax) {
+		stack[0] = kStackSentinel;
+		sp = 1;
+		node = sc.root;
+		best.t = tmax; best.ref = kNoHit; best.u = 0.f; best.v = 0.f;
+	}
+	__device__ __forceinline__ void park() { node = kStackSentinel; sp = 0; }
+	__device__ __forceinline__ bool done() const { return node == kStackSentinel; }
+	__device__ __forceinline__ bool wants_node() const { return node >= 0; }
+	__device__ __forceinline__ bool wants_leaf() const { return node < 0 && node != kStackSentinel; }
+	__device__ __forceinline__ uint32_t pending_leaf_kind() const { return ((uint32_t)(-1 - node) >> 4) >> 25; }  // diagnostics only
+
+	// One internal node: AABB::hit (AABB.rs:58-113) for both children at once, near child first, far child pushed.
+	// Slab distances in fp32 as fma(plane, 1/d, -o/d) against boxes padded by 8 ulp of the origin range
+	// (scene_layout.cu build_nodes): conservative, never culls a true hit.  Precondition: wants_node().
+	// kTop > 0: the first kTop nodes (breadth-first order = the top levels of the tree) are read from the CTA's
+	// shared-memory copy `top`; one generic-address load serves both cases, so lanes do not diverge on it.
+	template <bool kCount, int kTop>
+	__device__ __forceinline__ void node_step(const DeviceScene& sc, const RayConsts& rc, int* stack, uint32_t* node_visits, const float4* top) {
+		const float4* np = reinterpret_cast<const float4*>(sc.nodes + node);
+		float4 xy0, xy1, z01;
+		int link0, link1;
+		if (kTop > 0) {
+			if (node < kTop) np = top + node * 4;
+			xy0 = np[0]; xy1 = np[1]; z01 = np[2];
+			const int2 link = *reinterpret_cast<const int2*>(np + 3);
+			link0 = link.x; link1 = link.y;
+		} else {
+			xy0 = __ldg(np); xy1 = __ldg(np + 1); z01 = __ldg(np + 2);
+			const int4 link = __ldg(reinterpret_cast<const int4*>(np + 3));
+			link0 = link.x; link1 = link.y;
+		}
+		if (kCount) ++(*node_visits);
+		float t0 = fmaf(xy0.x, rc.idx, -rc.oix), t1 = fmaf(xy0.y, rc.idx, -rc.oix);
+		float t2 = fmaf(xy0.z, rc.idy, -rc.oiy), t3 = fmaf(xy0.w, rc.idy, -rc.oiy);
+		float t4 = fmaf(z01.x, rc.idz, -rc.oiz), t5 = fmaf(z01.y, rc.idz, -rc.oiz);
+		const float en0 = fmaxf(fmaxf(fminf(t0, t1), fminf(t2, t3)), fmaxf(fminf(t4, t5), 0.0f));
+		const float ex0 = fminf(fminf(fmaxf(t0, t1), fmaxf(t2, t3)), fminf(fmaxf(t4, t5), rc.tmax32));
+		t0 = fmaf(xy1.x, rc.idx, -rc.oix); t1 = fmaf(xy1.y, rc.idx, -rc.oix);
+		t2 = fmaf(xy1.z, rc.idy, -rc.oiy); t3 = fmaf(xy1.w, rc.idy, -rc.oiy);
+		t4 = fmaf(z01.z, rc.idz, -rc.oiz); t5 = fmaf(z01.w, rc.idz, -rc.oiz);
+		const float en1 = fmaxf(fmaxf(fminf(t0, t1), fminf(t2, t3)), fmaxf(fminf(t4, t5), 0.0f));
+		const float ex1 = fminf(fminf(fmaxf(t0, t1), fmaxf(t2, t3)), fminf(fmaxf(t4, t5), rc.tmax32));
+		const bool h0 = en0 <= ex0, h1 = en1 <= ex1;
+#if GS_NODE_LOAD == 1
+		// Select form: both links are consumed unconditionally, so their load is issued with the box loads.  (In the
+		// branchy form below the compiler sinks the link load under the "some child hit" branch and every descent pays two
+		// dependent L1 round trips.)
+		const bool first0 = h0 && (!h1 || !(en1 < en0));
+		const int first = first0 ? link0 : link1, second = first0 ? link1 : link0;
+		if (h0 && h1) stack[sp++] = second;
+		if (h0 || h1) node = first;
+		else node = stack[--sp];
+#else
+		if (!h0 && !h1) { node = stack[--sp]; }
+		else {
+			int near = link0, far = link1;
+			if (h0 && h1) {
+				if (en1 < en0) { int tmp = near; near = far; far = tmp; }
+				stack[sp++] = far;
+				node = near;
+			} else node = h0 ? near : far;
+		}
+#endif
+	}
+
+	// The leaf under `node`, then pop.  Precondition: wants_leaf().
+	template <bool kTris>
+	__device__ __forceinline__ void leaf_step(const DeviceScene& sc, const Ray& r, RayConsts& rc, double tmin, int* stack) {
+		leaf_intersect<kTris>(sc, r, rc, tmin, best, node);
+		node = stack[--sp];
+	}
+};
+
+// ==========================================================================================
+// Traversal policy 2: the eight-wide compressed tree (DNode8).
+// State: the current NODE GROUP (`base` = child_base of the node it came from; `grp` bits 0-7 = its internal children that were
+// hit and are still to visit, stored at bit (slot ^ octinv) so that the highest set bit is the nearest in octant order; bits
+// 8-15 = that node's imask in slot order, needed to turn a slot into a child index), the pending LEAF hits of the node visited
+// last (`grp` bits 16-23, same bit order; `leaf_node` = that node), and a stack of (base, grp & 0xffff) pairs -- one entry per
+// node whose group still has unvisited members, i.e. at most one per level.
+// ==========================================================================================
+struct Trav8 {
+	static constexpr int kStackWords = 2 * kMaxStack8;
+	uint32_t base, grp, leaf_node;
+	int sp;      // stack WORDS in use (two per entry)
+	Hit best;
+
+	// bit a set where direction component a is >= 0, from the SIGN BIT (1 / d keeps it, and safe_rcp copies it for d = -0)
+	__device__ __forceinline__ static uint32_t octinv_bits(float x, float y, float z) {
+		return ((__float_as_uint(x) >> 31) | ((__float_as_uint(y) >> 31) << 1) | ((__float_as_uint(z) >> 31) << 2)) ^ 7u;
+	}
+	__device__ __forceinline__ static uint32_t octinv_of(const RayConsts& rc) { return octinv_bits(rc.idx, rc.idy, rc.idz); }
+	__device__ __forceinline__ void init(const DeviceScene&, const Ray& r, int*, double tmax) {
+		// a group holding only the root: base 0, imask bit 0, hit bit of slot 0
+		base = 0u; grp = (1u << 8) | (1u << octinv_bits((float)r.dx, (float)r.dy, (float)r.dz)); leaf_node = 0u; sp = 0;
+		best.t = tmax; best.ref = kNoHit; best.u = 0.f; best.v = 0.f;
+	}
+	__device__ __forceinline__ void park() { grp = 0u; sp = 0; }
+	__device__ __forceinline__ bool done() const { return (grp & 0x00ff00ffu) == 0u; }  // steps refill from the stack, so empty = finished
+	__device__ __forceinline__ bool wants_leaf() const { return (grp & 0x00ff0000u) != 0u; }
+	__device__ __forceinline__ bool wants_node() const { return (grp & 0x00ff00ffu) != 0u && (grp & 0x00ff0000u) == 0u; }
+	__device__ __forceinline__ uint32_t pending_leaf_kind() const { return 0u; }
+
+	__device__ __forceinline__ void refill(const int* stack) {  // nothing left in the current group: continue with the enclosing one
+		if ((grp & 0x00ff00ffu) == 0u) {
+			if (sp > 0) { sp -= 2; base = (uint32_t)stack[sp]; grp = (uint32_t)stack[sp + 1]; }
+			else grp = 0u;
+		}
+	}
+
+	// 32768 + q as a float: byte q goes to mantissa bits 8..15 of 0x47000000 (one PRMT, no integer-to-float conversion)
+	__device__ __forceinline__ static float qf(uint32_t word, int j) {
+		return __uint_as_float(__byte_perm(word, 0x47000000u, j == 0 ? 0x7404 : (j == 1 ? 0x7414 : (j == 2 ? 0x7424 : 0x7434))));
+	}
+
+	// Visit the nearest unvisited member of the current group: fetch it, test its eight children's boxes, and make their
+	// hits the new current group (the rest of the old one goes on the stack).  Precondition: wants_node().
+	// Slab distances: plane = corner + q * step, so t = q * (step / d) + (corner - o) / d; with q taken as (32768 + q) the
+	// constant absorbs -32768 * step / d (its rounding error, 2^-9 of a grid step, is covered by the builder's margin).
+	template <bool kCount, int kTop>
+	__device__ __forceinline__ void node_step(const DeviceScene& sc, const RayConsts& rc, int* stack, uint32_t* node_visits, const float4*) {
+		const uint32_t octinv = octinv_of(rc);
+		const uint32_t pos = 31u - __clz(grp & 0xffu);
+		grp &= ~(1u << pos);
+		const uint32_t slot = pos ^ octinv;
+		const uint32_t node = base + __popc((grp >> 8) & ((1u << slot) - 1u));
+		if (grp & 0xffu) { stack[sp] = (int)base; stack[sp + 1] = (int)(grp & 0xffffu); sp += 2; }
+		const uint4* np = reinterpret_cast<const uint4*>(sc.nodes8 + node);
+		const uint4 hd = __ldg(np), qx = __ldg(np + 1), qy = __ldg(np + 2), qz = __ldg(np + 3);
+		const uint2 tail = __ldg(reinterpret_cast<const uint2*>(np + 4) + 1);  // child_base, sphere_base: only child_base is used here
+		if (kCount) ++(*node_visits);
+		const float ax = __uint_as_float((hd.w & 0xffu) << 23) * rc.idx;
+		const float ay = __uint_as_float((hd.w & 0xff00u) << 15) * rc.idy;
+		const float az = __uint_as_float((hd.w & 0xff0000u) << 7) * rc.idz;
+		const float bx = fmaf(-32768.0f, ax, fmaf(__uint_as_float(hd.x), rc.idx, -rc.oix));
+		const float by = fmaf(-32768.0f, ay, fmaf(__uint_as_float(hd.y), rc.idy, -rc.oiy));
+		const float bz = fmaf(-32768.0f, az, fmaf(__uint_as_float(hd.z), rc.idz, -rc.oiz));
+		// near / far planes per axis by the sign of the direction: whole words (four children each)
+		const bool nx = !(octinv & 1u), ny = !(octinv & 2u), nz = !(octinv & 4u);
+		const uint32_t nearx[2] = {nx ? qx.z : qx.x, nx ? qx.w : qx.y}, farx[2] = {nx ? qx.x : qx.z, nx ? qx.y : qx.w};
+		const uint32_t neary[2] = {ny ? qy.z : qy.x, ny ? qy.w : qy.y}, fary[2] = {ny ? qy.x : qy.z, ny ? qy.y : qy.w};
+		const uint32_t nearz[2] = {nz ? qz.z : qz.x, nz ? qz.w : qz.y}, farz[2] = {nz ? qz.x : qz.z, nz ? qz.y : qz.w};
+		uint32_t hits = 0u;  // slot order
+#pragma unroll
+		for (int k = 0; k < 8; ++k) {
+			const int w = k >> 2, j = k & 3;
+			const float en = fmaxf(fmaxf(fmaf(qf(nearx[w], j), ax, bx), fmaf(qf(neary[w], j), ay, by)), fmaxf(fmaf(qf(nearz[w], j), az, bz), 0.0f));
+			const float ex = fminf(fminf(fmaf(qf(farx[w], j), ax, bx), fmaf(qf(fary[w], j), ay, by)), fminf(fmaf(qf(farz[w], j), az, bz), rc.tmax32));
+			if (en <= ex) hits |= 1u << k;
+		}
+		// internal hits to the low byte, leaf hits to the third byte, then slot k -> bit (k ^ octinv) in both at once
+		const uint32_t imask = hd.w >> 24;
+		uint32_t m = (hits & imask) | ((hits & ~imask) << 16);
+		if (octinv & 1u) m = ((m & 0x00550055u) << 1) | ((m >> 1) & 0x00550055u);
+		if (octinv & 2u) m = ((m & 0x00330033u) << 2) | ((m >> 2) & 0x00330033u);
+		if (octinv & 4u) m = ((m & 0x000f000fu) << 4) | ((m >> 4) & 0x000f000fu);
+		base = tail.x;
+		grp = m | (imask << 8);
+		leaf_node = node;
+		refill(stack);
+	}
+
+	// The pending leaf children of `leaf_node`, nearest first.  Precondition: wants_leaf().
+	template <bool kTris>
+	__device__ __forceinline__ void leaf_step(const DeviceScene& sc, const Ray& r, RayConsts& rc, double tmin, int* stack) {
+		const uint32_t octinv = octinv_of(rc);
+		const uint4 c4 = __ldg(reinterpret_cast<const uint4*>(sc.nodes8 + leaf_node) + 4);  // meta[0], meta[1], child_base, sphere_base
+		uint32_t pending = (grp >> 16) & 0xffu;
+		grp &= 0xffffu;
+		while (pending) {
+			const uint32_t pos = 31u - __clz(pending);
+			pending &= ~(1u << pos);
+			const uint32_t slot = pos ^ octinv;
+			const uint32_t meta = ((slot & 4u) ? c4.y : c4.x) >> ((slot & 3u) * 8u) & 0xffu;
+			const uint32_t kind = meta >> 6, off = meta & 63u;
+			int code;
+			if (kind == kKindSphere) code = leaf_code((kKindSphere << 25) | (c4.w + off), 0u);
+			else if (kind == 3u) code = __ldg(sc.leaf_links8 + leaf_node * 8u + slot);
+			else {
+				const uint2 c5 = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint4*>(sc.nodes8 + leaf_node) + 5));  // quad_base, tri_base
+				code = leaf_code((kind << 25) | ((kind == kKindQuad ? c5.x : c5.y) + off), 0u);
+			}
+			leaf_intersect<kTris>(sc, r, rc, tmin, best, code);
+		}
+		refill(stack);
+	}
+};
+
+// Closest hit over the surface BVH: BVHNode::hit + AABB::hit + HittableList::hit collapsed into an
+// ordered while-while traversal with a per-thread stack.  Result equals the reference's
+// unordered recursion (BVH.rs:68-90); exact ties follow the reference's visiting order (Q9).
+//
+// The traversal is RESUMABLE: its whole state is a Trav2 / Trav8 plus the stack, so the render megakernel
+// can leave the loop when enough lanes of the warp have finished their ray, shade / regenerate
+// those lanes, and re-enter with the unfinished rays exactly where they stopped (ncu on the first
+// version showed 8.4 of 32 lanes active in the node loop: lanes idled until the warp's longest ray ended).
+//
 // One round of the classic while-while traversal: descend to the next leaf, intersect it.
-// Precondition: tv.node != kStackSentinel.  kF: bit 0 = count node visits, bit 1 = scene holds triangles.
-template <int kF, int kTop = 0>
-__device__ __forceinline__ void trav_round(const DeviceScene& sc, const Ray& r, RayConsts& rc, double tmin, TravState& tv, int* stack,
+// Precondition: !tv.done().  kF: bit 0 = count node visits, bit 1 = scene holds triangles.
+template <int kF, int kTop, class Trav>
+__device__ __forceinline__ void trav_round(const DeviceScene& sc, const Ray& r, RayConsts& rc, double tmin, Trav& tv, int* stack,
                                            uint32_t* node_visits, const float4* top = nullptr) {
-	while (tv.node >= 0) node_step<(kF & 1) != 0, kTop>(sc, rc, tv, stack, node_visits, top);
-	if (tv.node != kStackSentinel) leaf_step<(kF & 2) != 0>(sc, r, rc, tmin, tv, stack);
+	while (tv.wants_node()) tv.template node_step<(kF & 1) != 0, kTop>(sc, rc, stack, node_visits, top);
+	if (tv.wants_leaf()) tv.template leaf_step<(kF & 2) != 0>(sc, r, rc, tmin, stack);
 }
 
-// Run-to-completion form (parity kernel, adaptive kernel, per-path hooks).
+// Run-to-completion form (parity kernel, adaptive tail kernel, per-path hooks).  kF bit 4 = the eight-wide tree.
 template <int kF>
 __device__ __forceinline__ Hit trace_closest(const DeviceScene& sc, const Ray& r, double tmin, double tmax, uint32_t* node_visits = nullptr) {
-	int stack[kMaxStack];
-	TravState tv;
-	trav_init(sc, tv, stack, tmax);
 	RayConsts rc = ray_consts(r, tmax);
-	while (tv.node != kStackSentinel) trav_round<kF>(sc, r, rc, tmin, tv, stack, node_visits);
-	return tv.best;
+	if (kF & 16) {
+		int stack[Trav8::kStackWords];
+		Trav8 tv;
+		tv.init(sc, r, stack, tmax);
+		while (!tv.done()) trav_round<kF, 0>(sc, r, rc, tmin, tv, stack, node_visits);
+		return tv.best;
+	} else {
+		int stack[Trav2::kStackWords];
+		Trav2 tv;
+		tv.init(sc, r, stack, tmax);
+		while (!tv.done()) trav_round<kF, 0>(sc, r, rc, tmin, tv, stack, node_visits);
+		return tv.best;
+	}
 }
 
 }  // namespace gs

@@ -1,0 +1,160 @@
+// grayshift_b200/csrc/gs_host.h -- host-side internals shared by abi.cu (entry points, launches), scene_layout.cu
+// (validation, re-layout of the flat scene description, the two trees, upload) and multi_gpu.cu.  Not part of the ABI.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/grayshift.h"
+#include "gs_internal.h"
+
+namespace gs {
+
+int fail(int code, const std::string& msg);
+#define GS_CUDA(call)                                                                                          \
+	do {                                                                                                       \
+		cudaError_t e_ = (call);                                                                               \
+		if (e_ != cudaSuccess) return ::gs::fail(GS_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+	} while (0)
+
+// Independent iterations over the host threads (scene creation of a 10^6-primitive scene spends its time in such loops);
+// small ranges stay on the calling thread.
+unsigned host_threads();
+template <class F> void parallel_for(size_t n, F&& body, size_t serial_below = 32768) {
+	const unsigned threads = host_threads();
+	if (n < serial_below || threads < 2) { for (size_t i = 0; i < n; ++i) body(i); return; }
+	std::vector<std::thread> pool;
+	const size_t chunk = (n + threads - 1) / threads;
+	for (unsigned t = 0; t < threads; ++t) {
+		const size_t lo = (size_t)t * chunk, hi = lo + chunk < n ? lo + chunk : n;
+		if (lo >= hi) break;
+		pool.emplace_back([lo, hi, &body]() { for (size_t i = lo; i < hi; ++i) body(i); });
+	}
+	for (auto& th : pool) th.join();
+}
+
+// Device memory comes from the device's stream-ordered pool with the release threshold lifted, so creating and
+// destroying scenes reuses the same HBM instead of mapping / unmapping it each time (cudaMalloc + cudaFree of a
+// 2.6 MB scene measured 25 + 55 ms per create/destroy pair next to a 226 ms render; from the pool it is < 1 ms).
+// Every allocation names the stream it is ordered on: the scene's upload stream for the immutable arrays (consumers wait
+// on gs_scene::ready), the caller's stream for per-render scratch (calls on different streams are chained through
+// gs_scene::last).
+cudaError_t dev_alloc(void** p, size_t bytes, cudaStream_t stream);
+void dev_free(void* p, cudaStream_t stream);
+
+template <class T> struct DevBuf {
+	T* p = nullptr;
+	size_t n = 0;
+	// grow-only scratch, ordered on `stream`
+	cudaError_t alloc(size_t count, cudaStream_t stream) {
+		if (count <= n && p) return cudaSuccess;
+		release(stream);
+		n = count;
+		return dev_alloc(reinterpret_cast<void**>(&p), n * sizeof(T), stream);
+	}
+	void release(cudaStream_t stream) { if (p) dev_free(p, stream); p = nullptr; n = 0; }
+};
+
+// Page-locked staging memory from a small process-wide pool (pinning 60 MB costs tens of milliseconds; a scene is created
+// per frame by callers that treat gs_scene_create + gs_render as one call).
+struct Staging {
+	uint8_t* p = nullptr;
+	size_t cap = 0;
+	int slot = -1;
+};
+cudaError_t staging_acquire(size_t bytes, Staging& out);
+void staging_release(Staging& s, cudaEvent_t busy_until);  // the block is reused once the event has completed
+void staging_forget_event(cudaEvent_t ev);                  // an event that is about to be destroyed no longer guards a block
+const char* last_error_cstr();
+
+constexpr int kCounterSlots = 64;
+constexpr size_t kSmallSceneBytes = 128u << 10;  // C1 (486 spheres) is 47 KB, C3 2 KB, C4 (the one that wants the spill-free build) 490 KB
+constexpr unsigned kAdaptiveTailPixels = 2048;   // adaptive renders: below this many unfinished pixels, switch to one warp per pixel
+constexpr int kStatSlots = 16;                   // [0..3] = gs_stats totals; [4..] only written by the GS_DIVERGENCE_STATS diagnostic build
+constexpr size_t kWideMinPrims = 16384;          // scenes with at least this many primitives traverse the eight-wide tree (override: GS_BVH_WIDTH)
+
+}  // namespace gs
+
+struct gs_scene {
+	int device = 0;
+	int sm_count = 0;
+	cudaStream_t up = nullptr;    // uploads and allocations of the immutable arrays
+	cudaEvent_t ready = nullptr;  // recorded on `up` after the last upload; every entry makes its stream wait on it
+	cudaEvent_t last = nullptr;   // recorded after the work an entry issued: orders entries on different streams (scratch reuse)
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // gs_render's timing pair
+	bool last_valid = false;
+
+	// ---- host copies kept for (re)building node arrays: re-padding when a camera sits outside the assumed origin range,
+	// and the tree that was not built at creation (gs_scene_set_option "bvh_width")
+	std::vector<gs_bvh_node> h_nodes;
+	std::vector<int> h_node_to_dnode;   // ABI node -> DNode index (internal nodes), -1 for leaves
+	std::vector<int> h_leaf_code;       // ABI node -> leaf code (leaves)
+	std::vector<int> h_bfs;             // internal ABI nodes in BFS order (= binary device order)
+	// eight-wide topology: slot k of wide node h holds ABI node w_kids[8h + k] (-1 = empty), w_child_base[h] = wide index of its
+	// first internal kid, w_prim_base[3h + kind] = first device primitive of that kind among its single-primitive leaf kids
+	std::vector<int> w_kids;
+	std::vector<int> w_child_base;
+	std::vector<uint32_t> w_prim_base;
+	std::vector<int> h_leaf_direct;     // ABI leaf -> device primitive index if the leaf is one freshly placed primitive the wide node can address by offset, else -1
+	int wide_depth = 0;
+	double origin_limit = 0.0;
+	double max_abs_coord = 0.0;
+
+	// ---- device: one allocation for all immutable arrays except the node arrays
+	void* blob = nullptr;
+	size_t blob_bytes = 0;
+	gs::DNode* nodes = nullptr;        size_t n_dnodes = 0;
+	gs::DNode8* nodes8 = nullptr;      size_t n_dnodes8 = 0;
+	int* leaf_links8 = nullptr;
+	std::vector<gs_image> h_images;  // sizes/formats for validation of camera.hdri_image
+	gs::DeviceScene ds{};
+	bool wide = false;           // which tree the kernels traverse
+
+	// adaptive sampler: the two lists of pixels still sampling, their lengths, per-pixel (sum lum, sum lum^2)
+	gs::DevBuf<uint32_t> px_list[2];
+	gs::DevBuf<unsigned> px_count;
+	gs::DevBuf<double2> lum;
+
+	// render scratch
+	gs::DevBuf<float4> accum;
+	gs::DevBuf<float> out_rgb;
+	gs::DevBuf<unsigned> out_counts;
+	unsigned long long* counters = nullptr;  // kCounterSlots work counters   (allocated with the blob's stream)
+	unsigned long long* stats = nullptr;     // kStatSlots device totals
+	int next_counter = 0;
+	uint64_t launches = 0;
+	bool count_nodes = false;
+	bool has_triangles = false;  // selects the kernel variants that carry the triangle branch
+	bool small_scene = false;    // nodes + primitives fit the L1 with room to spare: the kernels built for one more CTA per SM
+	uint64_t h2d_bytes = 0;
+
+	// gs_render_multi: this device's accumulator (plain cudaMalloc: peers map it), a landing buffer for peers that cannot be mapped
+	float4* multi_accum = nullptr;
+	size_t multi_accum_n = 0;
+	gs::DevBuf<float4> multi_landing;
+
+	// wavefront pipeline: path pool (structure of arrays) + counters.  Off by default: measured against the
+	// megakernel on B200 it wins 6 % on C4 and loses ~2x on C1/C3; option "wavefront" = 1 enables it.
+	bool use_wavefront = false;
+	int pool_capacity = 1 << 20;  // in-flight paths (112 B each)
+	gs::DevBuf<double4> pool_org, pool_dir;
+	gs::DevBuf<float4> pool_thr, pool_rad;
+	gs::DevBuf<uint4> pool_ids, pool_hit;
+	gs::DevBuf<int> free_list;
+	gs::DevBuf<gs::WaveCounters> wave_ctr;
+	gs::WaveCounters* h_wave_ctr = nullptr;  // pinned
+
+	~gs_scene();
+};
+
+namespace gs {
+int validate_desc(const gs_scene_desc* d);
+// Re-layout + upload of everything but the node arrays; fills s->ds, the host topology and s->ready's predecessors.
+int layout_scene(gs_scene* s, const gs_scene_desc* d);
+// (Re)build the node array of the binary / eight-wide tree for ray origins within origin_limit of the world origin.
+int build_nodes2(gs_scene* s, double origin_limit);
+int build_nodes8(gs_scene* s, double origin_limit);
+int build_current_nodes(gs_scene* s, double origin_limit);  // whichever trees exist
+int select_tree(gs_scene* s, int width);                    // 2 or 8; builds the tree if it does not exist yet
+}  // namespace gs

@@ -20,6 +20,7 @@ struct RenderParams {
 	const unsigned* n_list;                // device-resident length of pixel_list (total_items is derived from it on the device)
 	double2* lum;                          // per pixel (sum of luminance, sum of its square), camera.rs:132-133,146-147
 	bool small_scene;                      // nodes + primitives <= kSmallSceneBytes: the launch takes the 6-CTAs-per-SM build
+	bool wide;                             // traverse sc.nodes8 (eight-wide tree) instead of sc.nodes
 };
 
 struct AdaptiveParams {  // the stop test of camera.rs:150-164
@@ -46,7 +47,7 @@ struct AdaptiveTailParams {  // the last few pixels: one warp per pixel runs the
 // launch wrappers (defined next to the kernels); all asynchronous on `stream`
 cudaError_t launch_render_fixed(const RenderParams& p, int sm_count, bool count_nodes, bool triangles, cudaStream_t stream);
 cudaError_t launch_adaptive_init(uint32_t* list, unsigned* n_list, unsigned pixel_begin, unsigned pixel_stride, unsigned n_pixels, cudaStream_t stream);
-cudaError_t launch_adaptive_tail(const AdaptiveTailParams& p, unsigned n_upper, int sm_count, cudaStream_t stream);
+cudaError_t launch_adaptive_tail(const AdaptiveTailParams& p, unsigned n_upper, int sm_count, bool wide, cudaStream_t stream);
 cudaError_t launch_adaptive_decide(const AdaptiveParams& p, const uint32_t* list, const unsigned* n_in, uint32_t* next, unsigned* n_out,
                                    const double2* lum, cudaStream_t stream);
 cudaError_t launch_resolve(const float4* accum, int n_pixels, float* out_rgb, unsigned* out_counts, cudaStream_t stream);
@@ -54,10 +55,22 @@ cudaError_t launch_resolve_rgb8(const float4* accum, int n_pixels, unsigned char
 cudaError_t launch_camera_rays(const DCamera& cam, unsigned long long seed, unsigned sample, int pixel_begin, int pixel_end, double* rays_out,
                                cudaStream_t stream);
 cudaError_t launch_path_radiance(const DeviceScene& sc, const DCamera& cam, unsigned long long seed, const unsigned* pixel,
-                                 const unsigned* sample, size_t n, float* out_rgb, cudaStream_t stream);
+                                 const unsigned* sample, size_t n, float* out_rgb, bool wide, cudaStream_t stream);
+// exact = the parity build (trace_closest.cu: -fmad=false, IEEE division / square root); otherwise the render kernels' own
+// arithmetic (render_kernels.cu: FMA contraction, rcp/rsqrt.approx.f64 + Newton) over the same rays
 cudaError_t launch_trace_closest(const DeviceScene& sc, const double* rays, size_t n, double tmin, double tmax, int* prim_id, double* t,
-                                 cudaStream_t stream);
+                                 bool wide, cudaStream_t stream);
+cudaError_t launch_trace_closest_fast(const DeviceScene& sc, const double* rays, size_t n, double tmin, double tmax, int* prim_id, double* t,
+                                      bool wide, cudaStream_t stream);
 int render_fixed_blocks_per_sm(bool count_nodes, bool triangles);
+
+// Multi-GPU resolve: the W*H float4 accumulators of up to kMaxPeers devices are summed while they are resolved -- the kernel runs
+// on one device and reads the others' buffers through peer-mapped pointers (NVLink / NVSwitch), so the cross-GPU sum, the division
+// by the sample count (camera.rs:167) and, for the byte output, write_color's transfer (color.rs:8-26) are one pass over the data.
+constexpr int kMaxPeers = 16;
+struct PeerAccums { const float4* acc[kMaxPeers]; int n; };
+cudaError_t launch_reduce_resolve(const PeerAccums& peers, int n_pixels, float* out_rgb, unsigned char* out_rgb8, unsigned* out_counts,
+                                  float4* sum_out, cudaStream_t stream);
 
 // ---- wavefront pipeline (wavefront_kernels.cu) -------------------------------------------------------
 // Path pool: structure of arrays in HBM, one slot per in-flight path, every field a 16-byte record so each

@@ -85,12 +85,15 @@ __device__ __forceinline__ f3 background(const DeviceScene& sc, const DCamera& c
 }
 
 // ---- Perlin (noise 0.9.0, restated; see oracle.cpp) on a shared-memory permutation table ------------
-// Ken Perlin's 12 edge gradients selected by hash & 15 (12..15 alias 0, 9, 1, 11), branch-free: the 16-way
-// switch was inlined 8 times per octave and made up a fifth of the kernel's code.
+// The 12 edge gradients selected by hash & 15, cases 12..15 repeating cases 0, 1, 9, 11 (gradient_dot_v of noise 0.9's
+// core::perlin::perlin_3d: 0|12, 1|13, 9|14, 11|15 -- the order of the "Improving Noise" paper, not the 13 <-> 14 swap
+// of Perlin's Java bit trick; the oracle restates the same table).  Branch-free: the 16-way switch was inlined 8 times
+// per octave and made up a fifth of the kernel's code.  The nibble table folds 12..15 onto 0, 1, 9, 11; for h < 12
+// the gradient is (+-u) + (+-v) with u = x or y, v = y or z and the signs in bits 0 and 1.
 __device__ __forceinline__ float perlin_grad(uint32_t h, float x, float y, float z) {
-	h &= 15u;
+	h = (uint32_t)(0xB910BA9876543210ull >> ((h & 15u) * 4u)) & 15u;
 	const float u = h < 8u ? x : y;
-	const float v = h < 4u ? y : ((h == 12u || h == 14u) ? x : z);
+	const float v = h < 4u ? y : z;
 	return ((h & 1u) ? -u : u) + ((h & 2u) ? -v : v);
 }
 __device__ __forceinline__ float perlin_get(const uint8_t* __restrict__ perm, double px, double py, double pz) {
@@ -124,6 +127,7 @@ struct Surface {
 	bool front, is_sphere;
 	int material;
 	int quad_index;     // >= 0: a quad, whose (u, v) = (alpha, beta) are computed from the hit point when a texture needs them
+	int sphere_index;   // is_sphere: index into sph_uvrot (an instance's RotateY, needed by sphere_uv only)
 };
 
 __device__ __forceinline__ f3 texture_value(const DeviceScene& sc, const uint8_t* __restrict__ perm, int tex, const Surface& s, uint32_t& tex_fetches) {
@@ -150,9 +154,15 @@ __device__ __forceinline__ f3 texture_value(const DeviceScene& sc, const uint8_t
 				u = (float)((s.px * a01.x + s.py * a01.y + s.pz * a23.x) - a23.y);
 				v = (float)((s.px * b01.x + s.py * b01.y + s.pz * b23.x) - b23.y);
 			}
-			if (s.is_sphere) {  // sphere_uv, sphere.rs:55-60
+			if (s.is_sphere) {  // sphere_uv, sphere.rs:55-60, on the OBJECT-space outward normal: Sphere::hit computes (u, v) before
+				// RotateY::hit turns the normal into world space (hittable.rs:179-211), so the baked rotation is undone here
+				float nx = s.n_out.x, nz = s.n_out.z;
+				if (sc.sph_uvrot) {  // null when no sphere of the scene sits under a RotateY
+					const float2 cs = __ldg(sc.sph_uvrot + s.sphere_index);
+					nx = cs.x * s.n_out.x - cs.y * s.n_out.z; nz = cs.y * s.n_out.x + cs.x * s.n_out.z;
+				}
 				float theta = acosf(fminf(fmaxf(-s.n_out.y, -1.0f), 1.0f));
-				float phi = atan2f(-s.n_out.z, s.n_out.x) + kPi;
+				float phi = atan2f(-nz, nx) + kPi;
 				u = phi * (0.5f / kPi); v = theta * (1.0f / kPi);
 			}
 			const DImage im = sc.images[head.y];
@@ -268,7 +278,8 @@ bool boundary_closest(const DeviceScene& sc, const DMedium& m, const Ray& r, dou
 	for (int k = 0; k < m.sph_count; ++k) {
 		DSphere s = load_sphere(sc.bnd_spheres, m.sph_first + k);
 		double t;
-		if (hit_sphere(s, sc.bnd_sph_path, m.sph_first + k, r, a, inv_a, lo, best, t)) { best = t; found = true; }
+		const bool moving = sc.bnd_sph_path[m.sph_first + k].w != 0.0;  // .w flags a moving boundary sphere
+		if (hit_sphere(s, sc.bnd_sph_path, m.sph_first + k, moving, r, a, inv_a, lo, best, t)) { best = t; found = true; }
 	}
 	for (int k = 0; k < m.quad_count; ++k) {
 		DQuad q = load_quad(sc.bnd_quads, m.quad_first + k);
@@ -288,8 +299,9 @@ __device__ __forceinline__ bool medium_event(const DeviceScene& sc, const DMediu
 		// roots of one quadratic.  hit(UNIVERSE) takes the near root (any finite value is inside (-MAX, MAX));
 		// hit([t1 + 1e-4, MAX)) re-tests the near root (fails) and takes the far one if it lies beyond t1 + 1e-4.
 		DSphere s = load_sphere(sc.bnd_spheres, m.sph_first);
-		double cx = s.cx, cy = s.cy, cz = s.cz, rad = s.r;
-		if (rad < 0.0) { double4 p = sc.bnd_sph_path[m.sph_first]; cx += r.time * p.x; cy += r.time * p.y; cz += r.time * p.z; rad = -rad; }
+		double cx = s.cx, cy = s.cy, cz = s.cz;
+		const double rad = s.r;
+		if (m.flags & 1) { double4 p = sc.bnd_sph_path[m.sph_first]; cx += r.time * p.x; cy += r.time * p.y; cz += r.time * p.z; }
 		double ocx = cx - r.ox, ocy = cy - r.oy, ocz = cz - r.oz;
 		double h = r.dx * ocx + r.dy * ocy + r.dz * ocz;
 		double c = (ocx * ocx + ocy * ocy + ocz * ocz) - rad * rad;
@@ -384,20 +396,23 @@ __device__ __forceinline__ bool segment_shade(const DeviceScene& sc, const DCame
 	if (h.ref != kNoHit) {
 		const uint32_t index = h.ref & kRefIndexMask;
 		s.px = ray.ox + ray.dx * h.t; s.py = ray.oy + ray.dy * h.t; s.pz = ray.oz + ray.dz * h.t;  // ray.at(t)
-		if (kTris && (h.ref >> kRefKindShift) == 2u) {
+		s.sphere_index = 0;
+		if (kTris && (h.ref >> kRefKindShift) == kKindTriangle) {
 			// Triangle: normal = (b - a) x (c - a), handed on UNNORMALISED exactly like triangle.rs:21,63 (Lambertian
 			// normalises it in its ONB; Metal and Dielectric reflect about it as it is)
 			const DTriangle tr = load_triangle(sc.tris, index);
 			n_out = mk3((float)(tr.e2y * tr.e1z - tr.e2z * tr.e1y), (float)(tr.e2z * tr.e1x - tr.e2x * tr.e1z), (float)(tr.e2x * tr.e1y - tr.e2y * tr.e1x));
 			s.is_sphere = false; s.u = h.u; s.v = h.v; s.quad_index = -1;
 			s.material = __ldg(sc.tri_aux + index).x;
-		} else if ((h.ref >> kRefKindShift) == 0u) {
+		} else if ((h.ref >> kRefKindShift) != kKindQuad) {  // sphere: stationary (kind 0) or moving (kind 3)
 			DSphere sp = load_sphere(sc.spheres, index);
-			double cx = sp.cx, cy = sp.cy, cz = sp.cz, rad = sp.r;
-			if (rad < 0.0) { double4 p = sc.sph_path[index]; cx += ray.time * p.x; cy += ray.time * p.y; cz += ray.time * p.z; rad = -rad; }
-			const float inv_r = 1.0f / (float)rad;  // outward_normal = (p - c) / r (sphere.rs:91), difference in f64, quotient in f32
+			double cx = sp.cx, cy = sp.cy, cz = sp.cz;
+			if ((h.ref >> kRefKindShift) == kKindMovingSphere) { double4 p = sc.sph_path[index]; cx += ray.time * p.x; cy += ray.time * p.y; cz += ray.time * p.z; }
+			// outward_normal = (p - c) / r with the SIGNED radius (sphere.rs:91: a negative radius turns the normal inward, the
+			// hollow-glass trick); difference in f64, quotient in f32
+			const float inv_r = 1.0f / (float)sp.r;
 			n_out = mk3((float)(s.px - cx) * inv_r, (float)(s.py - cy) * inv_r, (float)(s.pz - cz) * inv_r);
-			s.is_sphere = true; s.u = 0.f; s.v = 0.f; s.quad_index = -1;
+			s.is_sphere = true; s.u = 0.f; s.v = 0.f; s.quad_index = -1; s.sphere_index = (int)index;
 			s.material = __ldg(sc.sph_aux + index).x;
 		} else {
 			const double2* qp = reinterpret_cast<const double2*>(sc.quads + index);
@@ -409,7 +424,7 @@ __device__ __forceinline__ bool segment_shade(const DeviceScene& sc, const DCame
 	} else {  // medium event: normal (1,0,0), u = v = 0, phase function as the material (volume.rs:54-62, Q10)
 		s.px = ray.ox + ray.dx * tmax; s.py = ray.oy + ray.dy * tmax; s.pz = ray.oz + ray.dz * tmax;
 		n_out = mk3(1.f, 0.f, 0.f);
-		s.is_sphere = false; s.u = 0.f; s.v = 0.f; s.quad_index = -1;
+		s.is_sphere = false; s.u = 0.f; s.v = 0.f; s.quad_index = -1; s.sphere_index = 0;
 		s.material = sc.media[medium_hit].phase_mat;
 	}
 	s.front = dot(d_in, n_out) < 0.0f;  // HitRecord::new, hittable.rs:35-36

@@ -54,12 +54,15 @@ constexpr int kMinShade = GS_MIN_SHADE;
 constexpr int kBail = GS_BAIL;
 
 // kF: bit 0 = count BVH node visits, bit 1 = the scene holds triangles, bit 2 = one batch of the adaptive sampler (work items
-// come from a device-resident list of the pixels still sampling, and the luminance sums of camera.rs:146-147 are kept)
+// come from a device-resident list of the pixels still sampling, and the luminance sums of camera.rs:146-147 are kept),
+// bit 4 = traverse the eight-wide compressed tree (DNode8 / Trav8) instead of the binary one -- chosen per scene by
+// gs_scene_create: a large scene's binary nodes come from L2 and every fetch is a dependent round trip
 // bit 3 = the scene's nodes and primitives fit the L1 several times over: one more CTA per SM (80 registers, some spills into the
 // shading code) -- measured +3...4 % on C1 / C3 and -3 % on C4, whose 0.5 MB working set feels the spills in the L1
 template <int kF>
 __global__ void __launch_bounds__(kBlock, (kF & 8) ? GS_MIN_BLOCKS + 1 : GS_MIN_BLOCKS) render_fixed_kernel(const __grid_constant__ RenderParams P) {
 	constexpr bool kAdaptive = (kF & 4) != 0;
+	using Trav = typename std::conditional<(kF & 16) != 0, Trav8, Trav2>::type;
 	const unsigned long long total_items = kAdaptive ? (unsigned long long)__ldg(P.n_list) * P.sample_count : P.total_items;
 	__shared__ uint8_t s_perm[256];
 	__shared__ float4 s_top[kTopNodes > 0 ? kTopNodes * 4 : 1];
@@ -71,10 +74,10 @@ __global__ void __launch_bounds__(kBlock, (kF & 8) ? GS_MIN_BLOCKS + 1 : GS_MIN_
 	PathCounters pc = {0u, 0u, 0u};
 	PathState st;
 	int state = kDead;
-	TravState tv;
-	tv.node = kStackSentinel; tv.sp = 0;
+	Trav tv;
+	tv.park();
 	int seg_medium = -1;
-	int stack[kMaxStack];
+	int stack[Trav::kStackWords];
 	// The kernel is register-bound (96 registers = 20 warps per SM), so what is touched once per PATH lives in shared
 	// memory instead of in registers held through every traversal: the lane's running sum for its current pixel
 	// (float4 + pixel id, [field][thread]: conflict-free) and the warp's current chunk of work items [next, end) with
@@ -163,7 +166,7 @@ __global__ void __launch_bounds__(kBlock, (kF & 8) ? GS_MIN_BLOCKS + 1 : GS_MIN_
 		if (state == kSetup) {
 			double seg_tmax;
 			if (segment_begin(P.sc, P.cam, st, pc, seg_tmax, seg_medium)) {
-				trav_init(P.sc, tv, stack, seg_tmax);
+				tv.init(P.sc, st.ray, stack, seg_tmax);
 				state = kTraverse;
 			} else finish_path();  // depth exhausted; the lane picks up new work in the next phase A
 		}
@@ -185,20 +188,20 @@ __global__ void __launch_bounds__(kBlock, (kF & 8) ? GS_MIN_BLOCKS + 1 : GS_MIN_
 			const bool trav = state == kTraverse;
 			for (;;) {
 				for (;;) {
-					const bool step = trav && tv.node >= 0;
+					const bool step = trav && tv.wants_node();
 					const unsigned ms = __ballot_sync(kFull, step);
 					if (ms == 0u) break;
-					const unsigned mw = __ballot_sync(kFull, trav && tv.node < 0 && tv.node != kStackSentinel);
+					const unsigned mw = __ballot_sync(kFull, trav && tv.wants_leaf());
 					c_iter += 1; c_step += __popc(ms); c_wait += __popc(mw); c_done += 32 - __popc(ms) - __popc(mw);
-					if (step) node_step<(kF & 1) != 0, kTopNodes>(P.sc, rc, tv, stack, &pc.node_visits, s_top);
+					if (step) tv.template node_step<(kF & 1) != 0, kTopNodes>(P.sc, rc, stack, &pc.node_visits, s_top);
 				}
-				const bool leaf = trav && tv.node < 0 && tv.node != kStackSentinel;
+				const bool leaf = trav && tv.wants_leaf();
 				const unsigned ml = __ballot_sync(kFull, leaf);
 				if (ml == 0u) break;
-				const unsigned kind = leaf ? (((uint32_t)(-1 - tv.node) >> 4) >> 25) : 9u;
+				const unsigned kind = leaf ? tv.pending_leaf_kind() : 9u;
 				const unsigned m0 = __ballot_sync(kFull, kind == 0u);
 				l_round += 1; l_sph += __popc(m0); l_quad += __popc(ml) - __popc(m0); l_done += 32 - __popc(ml);
-				if (leaf) leaf_step<(kF & 2) != 0>(P.sc, st.ray, rc, 0.001, tv, stack);
+				if (leaf) tv.template leaf_step<(kF & 2) != 0>(P.sc, st.ray, rc, 0.001, stack);
 			}
 			if (trav) state = kShade;
 			if (lane == 0) {
@@ -210,7 +213,7 @@ __global__ void __launch_bounds__(kBlock, (kF & 8) ? GS_MIN_BLOCKS + 1 : GS_MIN_
 #elif GS_MIN_SHADE >= 32
 		// Every lane runs its ray to completion (classic while-while); measured best on B200.
 		if (state == kTraverse) {
-			while (tv.node != kStackSentinel) trav_round<kF, kTopNodes>(P.sc, st.ray, rc, 0.001, tv, stack, &pc.node_visits, s_top);
+			while (!tv.done()) trav_round<kF, kTopNodes>(P.sc, st.ray, rc, 0.001, tv, stack, &pc.node_visits, s_top);
 			state = kShade;
 		}
 #else
@@ -232,17 +235,17 @@ __global__ void __launch_bounds__(kBlock, (kF & 8) ? GS_MIN_BLOCKS + 1 : GS_MIN_
 			// a round lasts as long as the kBail-th slowest lane needs, not the slowest.  The stragglers sit out the leaf
 			// phase and carry on in the next round.  (A fully converged loop with two ballots per node step was measured
 			// 10-15 % slower than the classic loop: 12 more instructions per step, and ptxas spilled the ray constants.)
-			if (trav && tv.node >= 0) {
-				do node_step<(kF & 1) != 0, kTopNodes>(P.sc, rc, tv, stack, &pc.node_visits, s_top);
-				while (tv.node >= 0 && __popc(__activemask()) > kBail);
+			if (trav && tv.wants_node()) {
+				do tv.template node_step<(kF & 1) != 0, kTopNodes>(P.sc, rc, stack, &pc.node_visits, s_top);
+				while (tv.wants_node() && __popc(__activemask()) > kBail);
 			}
 			__syncwarp();
-			const bool leaf = trav && tv.node < 0 && tv.node != kStackSentinel;
-			const unsigned m_live = __ballot_sync(kFull, leaf || (trav && tv.node >= 0));
+			const bool leaf = trav && tv.wants_leaf();
+			const unsigned m_live = __ballot_sync(kFull, trav && !tv.done());
 			if (n_trav0 - __popc(m_live) >= exit_at) break;
-			if (leaf) leaf_step<(kF & 2) != 0>(P.sc, st.ray, rc, 0.001, tv, stack);
+			if (leaf) tv.template leaf_step<(kF & 2) != 0>(P.sc, st.ray, rc, 0.001, stack);
 		}
-		if (state == kTraverse && tv.node == kStackSentinel) state = kShade;
+		if (state == kTraverse && tv.done()) state = kShade;
 #endif
 	}
 	flush_pixel();
@@ -304,6 +307,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 	return v;
 }
 
+template <int kF>  // 2 = binary tree, 18 = eight-wide tree (both with the triangle branch: this kernel is not the hot one)
 __global__ void __launch_bounds__(kBlock) adaptive_tail_kernel(const __grid_constant__ AdaptiveTailParams P) {
 	__shared__ uint8_t s_perm[256];
 	load_perm(s_perm, P.sc.perlin_perm);
@@ -340,7 +344,7 @@ __global__ void __launch_bounds__(kBlock) adaptive_tail_kernel(const __grid_cons
 					next += need < avail ? need : avail;
 				}
 				if (!__any_sync(kFull, alive)) break;
-				if (alive && path_step<2>(P.sc, P.cam, s_perm, st, pc)) {
+				if (alive && path_step<kF>(P.sc, P.cam, s_perm, st, pc)) {
 					cr += (double)st.L.x; cg += (double)st.L.y; cb += (double)st.L.z;
 					const double lum = 0.299 * (double)st.L.x + 0.587 * (double)st.L.y + 0.144 * (double)st.L.z;  // color.rs:31-33
 					sum += lum; sq_sum += lum * lum;
@@ -389,6 +393,35 @@ __global__ void resolve_rgb8_kernel(const float4* __restrict__ accum, int n_pixe
 	if (out_counts) out_counts[i] = (unsigned)a.w;
 }
 
+// Cross-GPU sum fused with the resolve: acc[0] is local, acc[1..] are the peers' accumulators read over NVLink (one coalesced
+// 128-bit load per pixel and device); optional outputs: linear mean radiance, the PPM bytes of write_color, counts, the summed
+// accumulator itself.
+__global__ void reduce_resolve_kernel(const __grid_constant__ PeerAccums P, int n_pixels, float* __restrict__ out_rgb, uchar3* __restrict__ out_rgb8,
+                                      unsigned* __restrict__ out_counts, float4* __restrict__ sum_out) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_pixels) return;
+	float4 a = P.acc[0][i];
+	for (int d = 1; d < P.n; ++d) {
+		const float4 b = P.acc[d][i];
+		a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+	}
+	if (sum_out) sum_out[i] = a;
+	const float inv = a.w > 0.f ? 1.0f / a.w : 0.f;
+	const float c[3] = {a.x * inv, a.y * inv, a.z * inv};
+	if (out_rgb) { out_rgb[i * 3 + 0] = c[0]; out_rgb[i * 3 + 1] = c[1]; out_rgb[i * 3 + 2] = c[2]; }
+	if (out_rgb8) {
+		unsigned char q[3];
+#pragma unroll
+		for (int k = 0; k < 3; ++k) {
+			double g = c[k] > 0.0f ? sqrt((double)c[k]) : 0.0;  // linear_to_gamma
+			g = g < 0.0 ? 0.0 : (g > 0.999 ? 0.999 : g);          // INTENSITY.clamp
+			q[k] = (unsigned char)(int)(256.0 * g);
+		}
+		out_rgb8[i] = make_uchar3(q[0], q[1], q[2]);
+	}
+	if (out_counts) out_counts[i] = (unsigned)a.w;
+}
+
 __global__ void camera_rays_kernel(const __grid_constant__ DCamera cam, unsigned long long seed, unsigned sample, int pixel_begin, int pixel_end,
                                    double* __restrict__ rays_out) {
 	int n = pixel_begin + blockIdx.x * blockDim.x + threadIdx.x;
@@ -400,6 +433,7 @@ __global__ void camera_rays_kernel(const __grid_constant__ DCamera cam, unsigned
 	o[0] = r.ox; o[1] = r.oy; o[2] = r.oz; o[3] = r.dx; o[4] = r.dy; o[5] = r.dz; o[6] = r.time;
 }
 
+template <int kF>
 __global__ void __launch_bounds__(kBlock) path_radiance_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ DCamera cam,
                                                                unsigned long long seed, const unsigned* __restrict__ pixel,
                                                                const unsigned* __restrict__ sample, size_t n, float* __restrict__ out_rgb) {
@@ -410,35 +444,29 @@ __global__ void __launch_bounds__(kBlock) path_radiance_kernel(const __grid_cons
 	PathCounters pc = {0u, 0u, 0u};
 	PathState st;
 	path_begin(st, cam, seed, pixel[k], sample[k]);
-	while (!path_step<2>(sc, cam, s_perm, st, pc)) {}
+	while (!path_step<kF>(sc, cam, s_perm, st, pc)) {}
 	out_rgb[k * 3 + 0] = st.L.x; out_rgb[k * 3 + 1] = st.L.y; out_rgb[k * 3 + 2] = st.L.z;
 }
 
 // ---- launch wrappers ------------------------------------------------------------------------------
-template <int kF>
-static void fixed_occupancy(int* n) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(n, render_fixed_kernel<kF>, kBlock, 0); }
-
 // kernel variant: bit 0 = count node visits, bit 1 = triangles, bit 2 = adaptive batch (never combined with bit 0),
-// bit 3 = small scene (never combined with bit 0)
+// bit 3 = small scene (never combined with bit 0 or bit 4), bit 4 = eight-wide tree
+#define GS_FIXED_VARIANTS(X) X(0) X(1) X(2) X(3) X(4) X(6) X(8) X(10) X(12) X(14) X(16) X(17) X(18) X(19) X(20) X(22)
+
 static int fixed_variant(const RenderParams& p, bool count_nodes, bool triangles) {
-	if (p.pixel_list) return 4 | (triangles ? 2 : 0) | (p.small_scene ? 8 : 0);
-	if (count_nodes) return 1 | (triangles ? 2 : 0);
-	return (triangles ? 2 : 0) | (p.small_scene ? 8 : 0);
+	const int wide = p.wide ? 16 : 0, small = (p.small_scene && !p.wide) ? 8 : 0;
+	if (p.pixel_list) return 4 | (triangles ? 2 : 0) | small | wide;
+	if (count_nodes) return 1 | (triangles ? 2 : 0) | wide;
+	return (triangles ? 2 : 0) | small | wide;
 }
 
 static int fixed_blocks_per_sm(int variant) {
 	int n = 0;
 	switch (variant) {
-		case 0: fixed_occupancy<0>(&n); break;
-		case 1: fixed_occupancy<1>(&n); break;
-		case 2: fixed_occupancy<2>(&n); break;
-		case 3: fixed_occupancy<3>(&n); break;
-		case 4: fixed_occupancy<4>(&n); break;
-		case 6: fixed_occupancy<6>(&n); break;
-		case 8: fixed_occupancy<8>(&n); break;
-		case 10: fixed_occupancy<10>(&n); break;
-		case 12: fixed_occupancy<12>(&n); break;
-		default: fixed_occupancy<14>(&n); break;
+#define X(v) case v: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, render_fixed_kernel<v>, kBlock, 0); break;
+		GS_FIXED_VARIANTS(X)
+#undef X
+		default: break;
 	}
 	return n > 0 ? n : 1;
 }
@@ -453,16 +481,10 @@ cudaError_t launch_render_fixed(const RenderParams& p, int sm_count, bool count_
 	unsigned long long grid = (unsigned long long)sm_count * per_sm;  // persistent: SMs x resident CTAs
 	if (blocks_needed < grid) grid = blocks_needed ? blocks_needed : 1;
 	switch (variant) {
-		case 0: render_fixed_kernel<0><<<(unsigned)grid, kBlock, 0, stream>>>(p); break;
-		case 1: render_fixed_kernel<1><<<(unsigned)grid, kBlock, 0, stream>>>(p); break;
-		case 2: render_fixed_kernel<2><<<(unsigned)grid, kBlock, 0, stream>>>(p); break;
-		case 3: render_fixed_kernel<3><<<(unsigned)grid, kBlock, 0, stream>>>(p); break;
-		case 4: render_fixed_kernel<4><<<(unsigned)grid, kBlock, 0, stream>>>(p); break;
-		case 6: render_fixed_kernel<6><<<(unsigned)grid, kBlock, 0, stream>>>(p); break;
-		case 8: render_fixed_kernel<8><<<(unsigned)grid, kBlock, 0, stream>>>(p); break;
-		case 10: render_fixed_kernel<10><<<(unsigned)grid, kBlock, 0, stream>>>(p); break;
-		case 12: render_fixed_kernel<12><<<(unsigned)grid, kBlock, 0, stream>>>(p); break;
-		default: render_fixed_kernel<14><<<(unsigned)grid, kBlock, 0, stream>>>(p); break;
+#define X(v) case v: render_fixed_kernel<v><<<(unsigned)grid, kBlock, 0, stream>>>(p); break;
+		GS_FIXED_VARIANTS(X)
+#undef X
+		default: return cudaErrorInvalidValue;
 	}
 	return cudaGetLastError();
 }
@@ -472,14 +494,16 @@ cudaError_t launch_adaptive_init(uint32_t* list, unsigned* n_list, unsigned pixe
 	return cudaGetLastError();
 }
 
-cudaError_t launch_adaptive_tail(const AdaptiveTailParams& p, unsigned n_upper, int sm_count, cudaStream_t stream) {
+cudaError_t launch_adaptive_tail(const AdaptiveTailParams& p, unsigned n_upper, int sm_count, bool wide, cudaStream_t stream) {
 	int per_sm = 0;
-	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, adaptive_tail_kernel, kBlock, 0);
+	if (wide) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, adaptive_tail_kernel<18>, kBlock, 0);
+	else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, adaptive_tail_kernel<2>, kBlock, 0);
 	if (per_sm < 1) per_sm = 1;
 	unsigned long long blocks_needed = ((unsigned long long)n_upper + (kBlock / 32) - 1) / (kBlock / 32);
 	unsigned long long grid = (unsigned long long)sm_count * per_sm;
 	if (blocks_needed < grid) grid = blocks_needed ? blocks_needed : 1;
-	adaptive_tail_kernel<<<(unsigned)grid, kBlock, 0, stream>>>(p);
+	if (wide) adaptive_tail_kernel<18><<<(unsigned)grid, kBlock, 0, stream>>>(p);
+	else adaptive_tail_kernel<2><<<(unsigned)grid, kBlock, 0, stream>>>(p);
 	return cudaGetLastError();
 }
 
@@ -501,6 +525,12 @@ cudaError_t launch_resolve_rgb8(const float4* accum, int n_pixels, unsigned char
 	return cudaGetLastError();
 }
 
+cudaError_t launch_reduce_resolve(const PeerAccums& peers, int n_pixels, float* out_rgb, unsigned char* out_rgb8, unsigned* out_counts,
+                                  float4* sum_out, cudaStream_t stream) {
+	reduce_resolve_kernel<<<(n_pixels + 255) / 256, 256, 0, stream>>>(peers, n_pixels, out_rgb, reinterpret_cast<uchar3*>(out_rgb8), out_counts, sum_out);
+	return cudaGetLastError();
+}
+
 cudaError_t launch_camera_rays(const DCamera& cam, unsigned long long seed, unsigned sample, int pixel_begin, int pixel_end, double* rays_out,
                                cudaStream_t stream) {
 	int n = pixel_end - pixel_begin;
@@ -510,10 +540,18 @@ cudaError_t launch_camera_rays(const DCamera& cam, unsigned long long seed, unsi
 }
 
 cudaError_t launch_path_radiance(const DeviceScene& sc, const DCamera& cam, unsigned long long seed, const unsigned* pixel,
-                                 const unsigned* sample, size_t n, float* out_rgb, cudaStream_t stream) {
+                                 const unsigned* sample, size_t n, float* out_rgb, bool wide, cudaStream_t stream) {
 	if (n == 0) return cudaSuccess;
-	path_radiance_kernel<<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, stream>>>(sc, cam, seed, pixel, sample, n, out_rgb);
+	const unsigned grid = (unsigned)((n + kBlock - 1) / kBlock);
+	if (wide) path_radiance_kernel<18><<<grid, kBlock, 0, stream>>>(sc, cam, seed, pixel, sample, n, out_rgb);
+	else path_radiance_kernel<2><<<grid, kBlock, 0, stream>>>(sc, cam, seed, pixel, sample, n, out_rgb);
 	return cudaGetLastError();
 }
 
 }  // namespace gs
+
+// The closest-hit batch kernel once more, with THIS translation unit's arithmetic (what the render kernels really run:
+// FMA contraction, approximate-plus-Newton f64 division / square root): gs_trace_closest_fast, the parity hook that shows
+// the timed code picks the same primitives as the contraction-free build.
+#define GS_TRACE_NAME trace_closest_fast
+#include "trace_closest_body.cuh"

@@ -67,13 +67,13 @@ __global__ void __launch_bounds__(kBlock) wf_traverse_kernel(const __grid_consta
 	const unsigned n = (unsigned)P.pool.n;
 	int slot = -1;
 	Ray ray;
-	TravState tv;
+	Trav2 tv;  // the wavefront pipeline walks the binary tree
 	RayConsts rc;
 	int medium = -1;
 	int stack[kMaxStack];
 	PathCounters pc = {0u, 0u, 0u};
 	bool drained = false;
-	tv.node = kStackSentinel; tv.sp = 0;
+	tv.park();
 
 	for (;;) {
 		const unsigned idle = __ballot_sync(kFull, slot < 0);
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(kBlock) wf_traverse_kernel(const __grid_consta
 							}
 							reinterpret_cast<uint32_t*>(P.pool.ids + s)[2] = rng.draw;
 						}
-						trav_init(P.sc, tv, stack, tmax);
+						tv.init(P.sc, ray, stack, tmax);
 						rc = ray_consts(ray, tmax);
 						slot = (int)s;
 					}
@@ -122,8 +122,8 @@ __global__ void __launch_bounds__(kBlock) wf_traverse_kernel(const __grid_consta
 			continue;
 		}
 		if (slot >= 0) {
-			trav_round<kF>(P.sc, ray, rc, 0.001, tv, stack, &pc.node_visits);
-			if (tv.node == kStackSentinel) {
+			trav_round<kF, 0>(P.sc, ray, rc, 0.001, tv, stack, &pc.node_visits);
+			if (tv.done()) {
 				// closest event: surface hit (ref), else medium event (t = the medium's candidate), else miss
 				reinterpret_cast<double*>(P.pool.dir + slot)[3] = tv.best.t;
 				P.pool.hit[slot] = make_uint4(tv.best.ref, (unsigned)medium, __float_as_uint(tv.best.u), __float_as_uint(tv.best.v));

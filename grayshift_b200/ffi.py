@@ -11,7 +11,7 @@ LIB_DIR = os.path.join(_HERE, "lib")
 REPO_ROOT = os.path.dirname(_HERE)
 ASSET_DIR = os.path.join(REPO_ROOT, "assets")
 
-GS_ABI_VERSION = 1
+GS_ABI_VERSION = 2
 GS_OK, GS_ERR_INVALID, GS_ERR_NO_DEVICE, GS_ERR_CUDA, GS_ERR_NCCL, GS_ERR_UNSUPPORTED = range(6)
 
 d3 = C.c_double * 3
@@ -19,7 +19,7 @@ d3 = C.c_double * 3
 
 class gs_sphere(C.Structure):
     _fields_ = [("center", d3), ("radius", C.c_double), ("path", d3), ("material", C.c_int32), ("prim_id", C.c_int32),
-                ("moving", C.c_int32), ("order", C.c_int32)]
+                ("moving", C.c_int32), ("order", C.c_int32), ("uv_rotation", C.c_double * 2)]
 
 
 class gs_quad(C.Structure):
@@ -84,7 +84,7 @@ class gs_sample_settings(C.Structure):
 class gs_stats(C.Structure):
     _fields_ = [("paths", C.c_uint64), ("rays", C.c_uint64), ("tex_fetches", C.c_uint64), ("node_visits", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("kernel_ms", C.c_double), ("total_ms", C.c_double),
-                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("exchange_ms", C.c_double)]
 
 
 # every symbol include/grayshift.h declares (tests check the library exports all of them)
@@ -96,15 +96,19 @@ CUDA_SYMBOLS = {
     "gs_scene_destroy": (None, [C.c_void_p]),
     "gs_render": (C.c_int, [C.c_void_p, C.POINTER(gs_camera), C.POINTER(gs_sample_settings), C.c_uint64, C.c_void_p, C.c_void_p,
                             C.POINTER(gs_stats)]),
+    "gs_render_multi": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(gs_camera), C.POINTER(gs_sample_settings), C.c_uint64, C.c_void_p,
+                                  C.c_void_p, C.POINTER(gs_stats)]),
     "gs_render_accumulate": (C.c_int, [C.c_void_p, C.POINTER(gs_camera), C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
     "gs_render_adaptive_accumulate": (C.c_int, [C.c_void_p, C.POINTER(gs_camera), C.POINTER(gs_sample_settings), C.c_uint64, C.c_uint32,
                                                 C.c_uint32, C.c_void_p, C.c_void_p]),
     "gs_scene_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
+    "gs_scene_get_info": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_int64)]),
     "gs_resolve": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gs_resolve_rgb8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gs_stats_read": (C.c_int, [C.c_void_p, C.POINTER(gs_stats)]),
     "gs_tonemap": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p]),
     "gs_trace_closest": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_double, C.c_double, C.c_void_p, C.c_void_p]),
+    "gs_trace_closest_fast": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_double, C.c_double, C.c_void_p, C.c_void_p]),
     "gs_camera_rays": (C.c_int, [C.c_void_p, C.POINTER(gs_camera), C.c_uint64, C.c_uint32, C.c_int32, C.c_int32, C.c_void_p]),
     "gs_path_radiance": (C.c_int, [C.c_void_p, C.POINTER(gs_camera), C.c_uint64, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
 }

@@ -88,6 +88,8 @@ struct Flattener {
 		g.material = material(s.material);
 		g.prim_id = s.prim_id;
 		g.moving = s.is_moving ? 1 : 0;
+		// Sphere::hit takes (u, v) from the object-space normal, before RotateY::hit rotates the normal (hittable.rs:179-211)
+		g.uv_rotation[0] = x.c; g.uv_rotation[1] = x.s;
 		return g;
 	}
 	gs_quad bake_quad(const Quad& q, const Xform& x) {

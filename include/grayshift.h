@@ -30,14 +30,14 @@
 extern "C" {
 #endif
 
-#define GS_ABI_VERSION 1
+#define GS_ABI_VERSION 2
 
 typedef enum gs_status {
 	GS_OK = 0,
 	GS_ERR_INVALID = 1,    /* malformed description (bad index, empty scene, NaN bounds ...) */
 	GS_ERR_NO_DEVICE = 2,  /* no usable CUDA device */
 	GS_ERR_CUDA = 3,       /* CUDA runtime error; message carries the CUDA error string */
-	GS_ERR_NCCL = 4,
+	GS_ERR_NCCL = 4,       /* gs_render_multi: a peer-to-peer / NCCL step between the devices failed */
 	GS_ERR_UNSUPPORTED = 5
 } gs_status;
 
@@ -46,12 +46,17 @@ typedef enum gs_status {
 /* Sphere::new_stationary / new_moving, src/hittable/sphere.rs:21-49.  center(time) = center + time*path. */
 typedef struct gs_sphere {
 	double center[3];
-	double radius;
+	double radius;     /* SIGNED, as handed to the constructor: outward_normal = (p - center) / radius (sphere.rs:91), so a
+	                    * negative radius turns the normal inward (the hollow-glass trick).  Zero is rejected. */
 	double path[3];    /* center_path (sphere.rs:44); zero when stationary */
 	int32_t material;  /* index into gs_scene_desc.materials */
 	int32_t prim_id;   /* caller's id, returned by gs_trace_closest */
 	int32_t moving;    /* is_moving (sphere.rs:14) */
 	int32_t order;     /* rank of this primitive in the reference's visiting order (see gs_quad.order) */
+	/* (cos, sin) of the RotateY angle this sphere was baked with, (1, 0) when it is not under a RotateY.  Sphere::hit
+	 * computes (u, v) from the OBJECT-space normal before RotateY::hit turns the normal into world space
+	 * (sphere.rs:95, hittable.rs:179-211), so image-textured spheres need the rotation undone for sphere_uv. */
+	double uv_rotation[2];
 } gs_sphere;
 
 /* Quad::new, src/hittable/quad.rs:25-38.  The library derives normal, w and d exactly as
@@ -216,6 +221,7 @@ typedef struct gs_stats {
 	double kernel_ms;       /* device time of the render kernels (CUDA events) */
 	double total_ms;        /* wall time of the call */
 	uint64_t h2d_bytes, d2h_bytes;
+	double exchange_ms;     /* gs_render_multi: device time of the cross-GPU sum + resolve on the first device; 0 otherwise */
 } gs_stats;
 
 typedef struct gs_scene gs_scene;
@@ -238,6 +244,18 @@ void gs_scene_destroy(gs_scene* scene);
 int gs_render(gs_scene* scene, const gs_camera* camera, const gs_sample_settings* settings, uint64_t seed,
               float* out_rgb, uint32_t* out_counts, gs_stats* stats);
 
+/* Camera::render (camera.rs:100) on SEVERAL GPUs from one host thread -- no process group, no Python in the loop.  scenes[g] is
+ * the same description created on device g (gs_scene_create once per device).  Fixed sample counts are split by sample index
+ * (device g of G takes [g*spp/G, (g+1)*spp/G) of every pixel: the Philox counter carries the global sample index, so the image does
+ * not depend on G); the adaptive sampler splits pixels (device g takes pixels g, g+G, ...: a pixel's batch loop stays on one device).
+ * The device of scenes[0] then sums the W*H float4 accumulators WHILE it resolves them: its resolve kernel reads the peers' buffers
+ * through peer-mapped pointers over NVLink / NVSwitch (cross-GPU sum + /count in one pass; where two devices cannot map each other
+ * the buffer is first copied with cudaMemcpyPeer).  With the environment variable GS_MULTI_REDUCE=nccl the sum is an ncclReduce over
+ * a communicator the library creates with ncclCommInitAll (libnccl is loaded on demand).  GS_ERR_NCCL reports a failure of that
+ * exchange step, whichever transport it used.  stats (optional): totals over the devices, kernel_ms = the slowest device.  Blocking. */
+int gs_render_multi(gs_scene* const* scenes, int n_scenes, const gs_camera* camera, const gs_sample_settings* settings,
+                    uint64_t seed, float* out_rgb, uint32_t* out_counts, gs_stats* stats);
+
 /* Multi-GPU building block (one process per GPU, samples split across ranks): adds samples
  * [sample_begin, sample_begin + sample_count) of every pixel into a caller-owned DEVICE buffer of
  * W*H float4 (sum r, sum g, sum b, count) on `cuda_stream` (a cudaStream_t, NULL = default stream).
@@ -254,8 +272,13 @@ int gs_render_adaptive_accumulate(gs_scene* scene, const gs_camera* camera, cons
                                   uint64_t seed, uint32_t pixel_begin, uint32_t pixel_stride, void* d_accum,
                                   void* cuda_stream);
 /* Options: "count_nodes" (0/1) switches to the kernel variant that counts BVH node fetches and texel reads;
- * "wavefront" (0/1) selects the wavefront pipeline for fixed-count renders; "pool_capacity" its path pool size. */
+ * "wavefront" (0/1) selects the wavefront pipeline for fixed-count renders; "pool_capacity" its path pool size;
+ * "bvh_width" (2 or 8) selects the tree the kernels traverse -- the binary tree or the eight-wide compressed tree
+ * the library derives from it (default: by scene size; the other tree is built on first request). */
 int gs_scene_set_option(gs_scene* scene, const char* key, int64_t value);
+/* Facts about the scene as laid out on the device: "bvh_width" (2 / 8, the tree in use), "nodes2" / "nodes8" (node counts of the
+ * binary tree, 0 until it has been built, and of the eight-wide topology), "wide_depth", "scene_bytes" (device bytes held). */
+int gs_scene_get_info(gs_scene* scene, const char* key, int64_t* value);
 /* d_accum (device, W*H float4) -> host mean radiance and counts; blocking on `cuda_stream`. */
 int gs_resolve(gs_scene* scene, const void* d_accum, int32_t width, int32_t height, float* out_rgb,
                uint32_t* out_counts, void* cuda_stream);
@@ -277,6 +300,10 @@ int gs_tonemap(const float* rgb, size_t n_pixels, uint8_t* out_rgb8);
  * FMA contraction. */
 int gs_trace_closest(gs_scene* scene, const double* rays, size_t n, double tmin, double tmax,
                      int32_t* prim_id, double* t);
+/* The same query answered by the RENDER kernels' build of the traversal (FMA contraction, approximate-plus-Newton f64
+ * division and square root): shows that the timed code picks the primitives the contraction-free build picks. */
+int gs_trace_closest_fast(gs_scene* scene, const double* rays, size_t n, double tmin, double tmax,
+                          int32_t* prim_id, double* t);
 
 /* Parity hooks for the stochastic parts (one Philox path (pixel, sample) each):
  * camera rays of get_ray (camera.rs:204-221) for pixels [pixel_begin, pixel_end), 7 doubles per ray. */

@@ -136,6 +136,13 @@ int orc_path_radiance(void* scene, uint64_t seed, const uint32_t* pixel, const u
 void orc_philox(const uint32_t* ctr, const uint32_t* key, uint32_t* out) { philox4x32_10(ctr, key, out); }
 void orc_perlin_table(uint32_t seed, uint8_t* out) { perlin_permutation_table(seed, out); }
 double orc_perlin_get(double x, double y, double z) { static Perlin p(0); return p.get(x, y, z); }
+void orc_xorshift_words(const uint8_t* seed16, size_t n, uint32_t* out) { xorshift_words(seed16, n, out); }
+// returns the index, or -1 when the word stream ran out; *used = words consumed
+int64_t orc_gen_index(const uint32_t* words, size_t n_words, uint32_t ubound, size_t* used) {
+	int64_t r = -1;
+	guard([&] { r = gen_index_from_words(words, n_words, ubound, used); });
+	return r;
+}
 double orc_reflectance(double cosine, double ri) { return Dielectric::reflectance(cosine, ri); }
 double orc_luminance(double r, double g, double b) { return luminance(Vec3(r, g, b)); }
 int orc_color_byte(double c) { return color_byte(c); }

@@ -19,10 +19,15 @@ bool g_triangle_respects_interval = false;
 // Published algorithm: PermutationTable::new(seed) seeds rand_xorshift::XorShiftRng from the
 // 16 bytes [1,0,0,0, seed_le x3] and Fisher-Yates-shuffles 0..=255 with rand 0.8's
 // SliceRandom::shuffle (gen_index -> UniformInt<u32>::sample_single, widening-multiply zone
-// rejection); hash = perm[perm[perm[x&255]^(y&255)]^(z&255)]; gradient = Ken Perlin's 12 edge
-// vectors picked by hash&15; quintic fade; result * 2/sqrt(3) clamped to [-1,1].
+// rejection); hash = perm[perm[perm[x&255]^(y&255)]^(z&255)]; gradient = the 12 edge vectors
+// picked by hash&15 with cases 12..15 repeating (1,1,0), (-1,1,0), (0,-1,1), (0,-1,-1) in the order
+// of Perlin's "Improving Noise" paper, i.e. 0|12, 1|13, 9|14, 11|15 as core::perlin::perlin_3d's
+// gradient_dot_v writes them (NOT the 12, 14 / 13 swap of Perlin's Java bit trick); quintic fade;
+// result * 2/sqrt(3) clamped to [-1,1].
+// Pinned pieces: XorShift against rand_xorshift's own test_xorshift_true_values (tests/test_oracle_kat.py);
+// gen_index's arithmetic against the first draw of rand 0.8's value_stability_slice.  The shuffle as a
+// whole, the gradient aliasing above and the table it yields stay unpinned.
 // =========================================================================================
-namespace {
 struct XorShift {
 	uint32_t x, y, z, w;
 	uint32_t next() {
@@ -43,7 +48,25 @@ uint32_t rand08_gen_index(XorShift& rng, uint32_t ubound) {
 		if (lo <= zone) return hi;
 	}
 }
-}  // namespace
+
+// KAT hooks (tests/test_oracle_kat.py): the generator from 16 seed bytes (rand_core's from_seed reads them as four
+// little-endian words; an all-zero seed is replaced), and gen_index over a caller-supplied word stream.
+void xorshift_words(const uint8_t seed[16], size_t n, uint32_t* out) {
+	auto le = [&](int i) { return (uint32_t)seed[i] | ((uint32_t)seed[i + 1] << 8) | ((uint32_t)seed[i + 2] << 16) | ((uint32_t)seed[i + 3] << 24); };
+	XorShift rng{le(0), le(4), le(8), le(12)};
+	if (!(rng.x | rng.y | rng.z | rng.w)) rng = XorShift{0x193a6754u, 0xa8a7d469u, 0x97830e05u, 0x113ba7bbu};
+	for (size_t i = 0; i < n; ++i) out[i] = rng.next();
+}
+uint32_t gen_index_from_words(const uint32_t* words, size_t n_words, uint32_t ubound, size_t* used) {
+	struct Stream { const uint32_t* w; size_t n, k; uint32_t next() { if (k >= n) throw std::runtime_error("gen_index: word stream exhausted"); return w[k++]; } } st{words, n_words, 0};
+	uint32_t range = ubound;
+	uint32_t zone = (range << __builtin_clz(range)) - 1u;
+	for (;;) {
+		uint32_t v = st.next();
+		uint64_t m = (uint64_t)v * range;
+		if ((uint32_t)m <= zone) { if (used) *used = st.k; return (uint32_t)(m >> 32); }
+	}
+}
 
 void perlin_permutation_table(uint32_t seed, uint8_t out[256]) {
 	uint8_t real[16] = {0};
@@ -67,7 +90,7 @@ Perlin::Perlin(uint32_t seed) { perlin_permutation_table(seed, perm); }
 static inline double perlin_grad3(unsigned h, double x, double y, double z) {
 	switch (h & 15u) {
 		case 0: case 12: return x + y;
-		case 1: case 14: return -x + y;
+		case 1: case 13: return -x + y;
 		case 2: return x - y;
 		case 3: return -x - y;
 		case 4: return x + z;
@@ -75,7 +98,7 @@ static inline double perlin_grad3(unsigned h, double x, double y, double z) {
 		case 6: return x - z;
 		case 7: return -x - z;
 		case 8: return y + z;
-		case 9: case 13: return -y + z;
+		case 9: case 14: return -y + z;
 		case 10: return y - z;
 		default: return -y - z;  // 11, 15
 	}

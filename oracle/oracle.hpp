@@ -350,6 +350,9 @@ struct Perlin {
 	double get(double px, double py, double pz) const;
 };
 void perlin_permutation_table(uint32_t seed, uint8_t out[256]);
+// KAT hooks for the third-party pieces behind the table (rand_xorshift 0.3, rand 0.8 gen_index); see oracle.cpp
+void xorshift_words(const uint8_t seed[16], size_t n, uint32_t* out);
+uint32_t gen_index_from_words(const uint32_t* words, size_t n_words, uint32_t ubound, size_t* used);
 
 // ---------------------------------------------------------------------------------------
 // Textures -- texture.rs:9-131

@@ -6,7 +6,7 @@ use std::process::Command;
 fn main() {
     let out = PathBuf::from(std::env::var("OUT_DIR").unwrap());
     let csrc = PathBuf::from(std::env::var("CARGO_MANIFEST_DIR").unwrap()).join("../grayshift_b200/csrc");
-    let units = [("abi.cu", false), ("render_kernels.cu", false), ("wavefront_kernels.cu", false), ("trace_closest.cu", true)];
+    let units = [("abi.cu", false), ("scene_layout.cu", false), ("render_kernels.cu", false), ("wavefront_kernels.cu", false), ("trace_closest.cu", true)];
     let mut objects = Vec::new();
     for (file, no_fma) in units {
         let obj = out.join(file.replace(".cu", ".o"));
@@ -24,7 +24,7 @@ fn main() {
     let mut link = Command::new("nvcc");
     link.args(["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static", "-o"]).arg(&lib).args(&objects);
     assert!(link.status().unwrap().success(), "nvcc link failed");
-    for h in ["gs_device.cuh", "gs_shade.cuh", "gs_kernel_util.cuh", "gs_internal.h"] {
+    for h in ["gs_device.cuh", "gs_shade.cuh", "gs_kernel_util.cuh", "gs_internal.h", "gs_host.h", "trace_closest_body.cuh"] {
         println!("cargo:rerun-if-changed={}", csrc.join(h).display());
     }
     println!("cargo:rustc-link-search=native={}", out.display());

@@ -5,7 +5,7 @@
 use std::ffi::CStr;
 use std::os::raw::{c_char, c_int, c_void};
 
-pub const GS_ABI_VERSION: u32 = 1;
+pub const GS_ABI_VERSION: u32 = 2;
 
 #[repr(C)]
 #[derive(Clone, Copy, Default)]
@@ -17,6 +17,7 @@ pub struct gs_sphere {
     pub prim_id: i32,
     pub moving: i32,
     pub order: i32,
+    pub uv_rotation: [f64; 2],
 }
 
 #[repr(C)]
@@ -183,6 +184,7 @@ pub struct gs_stats {
     pub total_ms: f64,
     pub h2d_bytes: u64,
     pub d2h_bytes: u64,
+    pub exchange_ms: f64,
 }
 
 #[repr(C)]
@@ -198,6 +200,9 @@ extern "C" {
     pub fn gs_scene_create(desc: *const gs_scene_desc, device: c_int, out: *mut *mut gs_scene) -> c_int;
     pub fn gs_scene_destroy(scene: *mut gs_scene);
     pub fn gs_scene_set_option(scene: *mut gs_scene, key: *const c_char, value: i64) -> c_int;
+    pub fn gs_scene_get_info(scene: *mut gs_scene, key: *const c_char, value: *mut i64) -> c_int;
+    pub fn gs_render_multi(scenes: *const *mut gs_scene, n_scenes: c_int, camera: *const gs_camera, settings: *const gs_sample_settings,
+                           seed: u64, out_rgb: *mut f32, out_counts: *mut u32, stats: *mut gs_stats) -> c_int;
     pub fn gs_render(scene: *mut gs_scene, camera: *const gs_camera, settings: *const gs_sample_settings, seed: u64,
                      out_rgb: *mut f32, out_counts: *mut u32, stats: *mut gs_stats) -> c_int;
     pub fn gs_render_accumulate(scene: *mut gs_scene, camera: *const gs_camera, seed: u64, sample_begin: u32, sample_count: u32,
@@ -213,6 +218,8 @@ extern "C" {
     pub fn gs_tonemap(rgb: *const f32, n_pixels: usize, out_rgb8: *mut u8) -> c_int;
     pub fn gs_trace_closest(scene: *mut gs_scene, rays: *const f64, n: usize, tmin: f64, tmax: f64, prim_id: *mut i32,
                             t: *mut f64) -> c_int;
+    pub fn gs_trace_closest_fast(scene: *mut gs_scene, rays: *const f64, n: usize, tmin: f64, tmax: f64, prim_id: *mut i32,
+                                 t: *mut f64) -> c_int;
     pub fn gs_camera_rays(scene: *mut gs_scene, camera: *const gs_camera, seed: u64, sample: u32, pixel_begin: i32,
                           pixel_end: i32, rays_out: *mut f64) -> c_int;
     pub fn gs_path_radiance(scene: *mut gs_scene, camera: *const gs_camera, seed: u64, pixel: *const u32, sample: *const u32,

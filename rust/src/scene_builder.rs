@@ -117,7 +117,9 @@ impl SceneBuilder {
     pub fn push_sphere(&mut self, xf: &Xform, center: [f64; 3], path: [f64; 3], moving: bool, radius: f64, material: i32) {
         let c = xf.point(center);
         let p = xf.rot(path);
-        let mut g = gs_sphere { center: c, radius, path: p, material, prim_id: self.next_prim_id, moving: moving as i32, order: 0 };
+        // uv_rotation: Sphere::hit takes (u, v) from the object-space normal, before RotateY::hit rotates it (hittable.rs:179-211)
+        let mut g = gs_sphere { center: c, radius, path: p, material, prim_id: self.next_prim_id, moving: moving as i32, order: 0,
+                                uv_rotation: [xf.c, xf.s] };
         self.next_prim_id += 1;
         if self.open_medium.is_some() {
             g.material = 0; // a boundary's own material is never used

@@ -43,6 +43,10 @@ def lib(counters=False):
         L.orc_perlin_table.argtypes = [C.c_uint32, C.c_void_p]
         L.orc_perlin_get.restype = C.c_double
         L.orc_perlin_get.argtypes = [C.c_double, C.c_double, C.c_double]
+        L.orc_xorshift_words.restype = None
+        L.orc_xorshift_words.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+        L.orc_gen_index.restype = C.c_int64
+        L.orc_gen_index.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p]
         L.orc_reflectance.restype = C.c_double
         L.orc_reflectance.argtypes = [C.c_double, C.c_double]
         L.orc_luminance.restype = C.c_double

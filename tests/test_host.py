@@ -44,8 +44,8 @@ def test_graph_roundtrip(tmp_path):
 
 def arrays(desc):
     d = desc.contents
-    sph = np.ctypeslib.as_array(C.cast(d.spheres, C.POINTER(C.c_double)), shape=(d.n_spheres, 9)).copy() if d.n_spheres else np.zeros((0, 9))
-    sph_i = np.ctypeslib.as_array(C.cast(d.spheres, C.POINTER(C.c_int32)), shape=(d.n_spheres, 18))[:, 14:18].copy() if d.n_spheres else np.zeros((0, 4), int)
+    sph = np.ctypeslib.as_array(C.cast(d.spheres, C.POINTER(C.c_double)), shape=(d.n_spheres, 11)).copy() if d.n_spheres else np.zeros((0, 11))
+    sph_i = np.ctypeslib.as_array(C.cast(d.spheres, C.POINTER(C.c_int32)), shape=(d.n_spheres, 22))[:, 14:18].copy() if d.n_spheres else np.zeros((0, 4), int)
     sph = sph[:, :7]
     quad = np.ctypeslib.as_array(C.cast(d.quads, C.POINTER(C.c_double)), shape=(d.n_quads, 11))[:, :9].copy() if d.n_quads else np.zeros((0, 9))
     quad_i = np.ctypeslib.as_array(C.cast(d.quads, C.POINTER(C.c_int32)), shape=(d.n_quads, 22))[:, 18:22].copy() if d.n_quads else np.zeros((0, 4), int)

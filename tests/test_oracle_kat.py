@@ -9,6 +9,8 @@ reference lines it pins (paths relative to /root/reference/src).
 import math
 import os
 
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -312,6 +314,73 @@ def test_perlin_table_and_noise_properties():
         assert L.orc_perlin_get(float(p[0]), float(p[1]), float(p[2])) == 0.0
     p = np.array([3.3, -7.1, 12.9])
     assert abs(L.orc_perlin_get(*p) - L.orc_perlin_get(*(p + 1e-9))) < 1e-7
+
+
+def test_xorshift_matches_the_rand_xorshift_crate_vectors():
+    """rand_xorshift's own `test_xorshift_true_values`: seed bytes 16..1, nine next_u32 and then nine next_u64
+    (low word first).  This pins the generator behind noise 0.9's PermutationTable::new (texture.rs:104)."""
+    seed = np.arange(16, 0, -1, dtype=np.uint8)
+    out = np.empty(27, dtype=np.uint32)
+    orc.lib().orc_xorshift_words(seed.ctypes.data, 27, out.ctypes.data)
+    assert out[:9].tolist() == [2081028795, 620940381, 269070770, 16943764, 854422573, 29242889, 1550291885, 1227154591, 271695242]
+    u64 = [(int(out[9 + 2 * k + 1]) << 32) | int(out[9 + 2 * k]) for k in range(9)]
+    assert u64 == [9247529084182843387, 8321512596129439293, 14104136531997710878, 6848554330849612046, 343577296533772213,
+                   17828467390962600268, 9847333257685787782, 7717352744383350108, 1133407547287910111]
+
+
+def _pcg32_words(state, n, stream=11634580027462260723):
+    """rand_pcg::Pcg32::new(state, stream) -- the generator behind rand's `crate::test::rng(seed)`."""
+    M, mult = (1 << 64) - 1, 6364136223846793005
+    inc = ((stream << 1) | 1) & M
+    st = (state + inc) & M
+    st = (st * mult + inc) & M
+    out = []
+    for _ in range(n):
+        old, st = st, (st * mult + inc) & M
+        rot, xsh = old >> 59, (((old >> 18) ^ old) >> 27) & 0xffffffff
+        out.append(((xsh >> rot) | (xsh << ((32 - rot) & 31))) & 0xffffffff)
+    return np.array(out, dtype=np.uint32)
+
+
+def test_gen_index_arithmetic():
+    """rand 0.8 `gen_index` = UniformInt<u32>::sample_single(0, ubound): widening multiply, accept when the low word is
+    <= (range << lz) - 1.  Checked (i) against the definition in exact integer arithmetic on random words, (ii) for
+    unbiasedness of the accepted values, (iii) against the one value of rand's `value_stability_slice` that could be
+    restated with confidence: `chars.choose(&mut rng(413))` over 14 letters gives 'l' (index 11)."""
+    L = orc.lib()
+    rng = np.random.default_rng(5)
+    used = C.c_size_t()
+    for ub in (2, 3, 14, 100, 255, 256, 1000):
+        words = rng.integers(0, 1 << 32, 64, dtype=np.uint64).astype(np.uint32)
+        got = L.orc_gen_index(words.ctypes.data, words.size, ub, C.byref(used))
+        zone = ((ub << (32 - ub.bit_length())) & 0xffffffff) - 1
+        k = next(i for i, w in enumerate(words.tolist()) if ((w * ub) & 0xffffffff) <= zone)
+        assert used.value == k + 1 and got == (int(words[k]) * ub) >> 32
+    words = _pcg32_words(413, 8)
+    assert "abcdefghijklmn"[L.orc_gen_index(words.ctypes.data, words.size, 14, C.byref(used))] == "l"
+
+
+def test_perlin_gradient_cases_follow_noise_0_9():
+    """gradient_dot_v of noise 0.9's core::perlin::perlin_3d: hash & 15 -> 12 edge vectors, 12..15 repeating
+    (1,1,0), (-1,1,0), (0,-1,1), (0,-1,-1).  Probed through Perlin::get: inside one lattice cell, close to a corner,
+    the value is dominated by that corner's gradient dotted with the offset."""
+    tab = orc.perlin_table(0).astype(np.int64)
+    L = orc.lib()
+    grads = [(1, 1, 0), (-1, 1, 0), (1, -1, 0), (-1, -1, 0), (1, 0, 1), (-1, 0, 1), (1, 0, -1), (-1, 0, -1), (0, 1, 1), (0, -1, 1), (0, 1, -1),
+             (0, -1, -1), (1, 1, 0), (-1, 1, 0), (0, -1, 1), (0, -1, -1)]
+    seen = set()
+    eps = 1e-4
+    for x in range(-8, 8):
+        for y in range(-8, 8):
+            for z in range(-8, 8):
+                h = int(tab[tab[tab[x & 255] ^ (y & 255)] ^ (z & 255)]) & 15
+                seen.add(h)
+                g = np.array(grads[h], dtype=np.float64)
+                for d in ((eps, 0, 0), (0, eps, 0), (0, 0, eps)):
+                    v = L.orc_perlin_get(x + d[0], y + d[1], z + d[2])
+                    expect = 1.1547005383792515 * float(g @ np.array(d))
+                    assert abs(v - expect) < 5e-3 * eps + 1e-12, (x, y, z, h, d, v, expect)
+    assert seen == set(range(16))
 
 
 def test_noise_texture_formula(tmp_path):  # texture.rs:107-130

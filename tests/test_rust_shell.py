@@ -42,7 +42,7 @@ def rust_structs():
 
 
 # (c_uint64 and c_size_t are one ctypes type on LP64: either Rust spelling has the right size; the names are checked too)
-RUST_TYPE = {C.c_double: {"f64"}, C.c_int32: {"i32"}, C.c_uint32: {"u32"}, C.c_uint64: {"u64", "usize"}, ffi.d3: {"[f64; 3]"}}
+RUST_TYPE = {C.c_double: {"f64"}, C.c_double * 2: {"[f64; 2]"}, C.c_int32: {"i32"}, C.c_uint32: {"u32"}, C.c_uint64: {"u64", "usize"}, ffi.d3: {"[f64; 3]"}}
 
 
 def test_every_header_function_is_declared_in_the_rust_ffi_with_the_same_arity():
