@@ -729,25 +729,35 @@ int build_nodes8(gs_scene* s, double origin_limit) {
 		}
 		DNode8 d;
 		std::memset(&d, 0, sizeof d);
-		d.px = corner[0]; d.py = corner[1]; d.pz = corner[2];
 		uint32_t q[3][4];  // per axis: lo[0..3], lo[4..7], hi[0..3], hi[4..7]; empty slots lo = 255 > hi = 0
 		for (int a = 0; a < 3; ++a) { q[a][0] = q[a][1] = 0xffffffffu; q[a][2] = q[a][3] = 0u; }
 		uint32_t exps = 0;
+		// Every stored plane lies at least `margin` of a grid step outside the box it bounds -- the lowest one too, which is
+		// why the node's corner sits two margins below the lowest child plane: the decode's bias constant (Trav8::qf) is
+		// off by up to 2^-9 of a step, and with an axis-parallel ray (1/d = 1e25) that error decides hit or miss outright.
 		const double margin = 1.0 / 64.0;
 		for (int a = 0; a < 3; ++a) {
-			double extent = 0.0;
-			for (int k = 0; k < 8; ++k) if (kids[k] >= 0) extent = std::fmax(extent, (double)hi[k][a] - (double)corner[a]);
-			int e = -100;  // grid step 2^e: the smallest power of two with 255 steps >= extent (never below 2^-100)
-			if (extent > 0.0) e = std::max(e, (int)std::ceil(std::log2(extent / 254.0)));
-			while (std::ceil(extent / std::ldexp(1.0, e) + margin) > 255.0) ++e;
+			double top = -INFINITY;
+			for (int k = 0; k < 8; ++k) if (kids[k] >= 0) top = std::fmax(top, (double)hi[k][a]);
+			int e = -100;  // grid step 2^e: the smallest power of two whose 255 steps span the children (never below 2^-100)
+			const double extent0 = top - (double)corner[a];
+			if (extent0 > 0.0) e = std::max(e, (int)std::ceil(std::log2(extent0 / 250.0)));
+			float origin;
+			for (;; ++e) {
+				const double step = std::ldexp(1.0, e);
+				origin = float_down((double)corner[a] - 2.0 * margin * step);
+				if (std::ceil((top - (double)origin) / step + margin) <= 255.0) break;
+			}
 			if (e + 127 < 1 || e + 127 > 254) { bad = 1; return; }
 			exps |= (uint32_t)(e + 127) << (8 * a);
+			(a == 0 ? d.px : (a == 1 ? d.py : d.pz)) = origin;
 			const double inv_step = std::ldexp(1.0, -e);
 			for (int k = 0; k < 8; ++k) {
 				if (kids[k] < 0) continue;
-				const double ql = std::floor(((double)lo[k][a] - (double)corner[a]) * inv_step - margin);
-				const double qh = std::ceil(((double)hi[k][a] - (double)corner[a]) * inv_step + margin);
-				const uint32_t bl = (uint32_t)std::min(255.0, std::max(0.0, ql)), bh = (uint32_t)std::min(255.0, std::max(0.0, qh));
+				const double ql = std::floor(((double)lo[k][a] - (double)origin) * inv_step - margin);
+				const double qh = std::ceil(((double)hi[k][a] - (double)origin) * inv_step + margin);
+				if (ql < 0.0 || qh > 255.0) { bad = 3; return; }
+				const uint32_t bl = (uint32_t)ql, bh = (uint32_t)qh;
 				const int w = k >> 2, sh = 8 * (k & 3);
 				q[a][w] = (q[a][w] & ~(0xffu << sh)) | (bl << sh);
 				q[a][2 + w] = (q[a][2 + w] & ~(0xffu << sh)) | (bh << sh);
@@ -782,6 +792,7 @@ int build_nodes8(gs_scene* s, double origin_limit) {
 	});
 	if (bad.load() == 1) return fail(GS_ERR_UNSUPPORTED, "eight-wide tree: box extent out of the fp32 exponent range");
 	if (bad.load() == 2) return fail(GS_ERR_CUDA, "eight-wide tree: internal error (leaf offset)");
+	if (bad.load() == 3) return fail(GS_ERR_CUDA, "eight-wide tree: internal error (plane outside the grid)");
 	const size_t bytes = node_bytes + link_bytes;
 	int rc = upload_nodes(s, reinterpret_cast<void**>(&s->nodes8), bytes, stg);
 	if (rc) return rc;

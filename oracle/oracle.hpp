@@ -428,14 +428,27 @@ struct Isotropic : Material {                                              // ma
 // ---------------------------------------------------------------------------------------
 // Hittables -- hittable/*.rs
 // ---------------------------------------------------------------------------------------
+// The reference clones an Arc<dyn Material> into every accepted candidate hit (sphere.rs:102, quad.rs:105, volume.rs:59): an
+// atomic increment / decrement pair on a counter shared by every thread that touches the same material (one Lambertian on 2400
+// quads in the final scene).  The timing build keeps that; ORC_NO_REFCOUNT (liboracle_norc.so) replaces the handle by a plain
+// pointer to show how much of the baseline's time is that contention (bench.py's cpu_baseline.no_refcount).
+#ifdef ORC_NO_REFCOUNT
+struct MaterialRef {
+	const Material* p;
+	MaterialRef(const std::shared_ptr<Material>& m) : p(m.get()) {}
+	const Material* operator->() const { return p; }
+};
+#else
+using MaterialRef = std::shared_ptr<Material>;
+#endif
 struct HitRecord {                                                         // hittable.rs:15-43
 	double t;
 	Vec3 position, normal;
 	bool is_front_face;
-	std::shared_ptr<Material> material;  // Arc clone per accepted candidate, as the reference does
+	MaterialRef material;  // Arc clone per accepted candidate, as the reference does
 	double u, v;
 	int prim_id;                         // oracle bookkeeping: construction-order primitive id (media: -2 - medium index)
-	HitRecord(const Ray& ray, double t_, const Vec3& pos, const Vec3& n, std::shared_ptr<Material> m,
+	HitRecord(const Ray& ray, double t_, const Vec3& pos, const Vec3& n, MaterialRef m,
 	          double u_, double v_, int pid)
 		: t(t_), position(pos), material(std::move(m)), u(u_), v(v_), prim_id(pid) {
 		is_front_face = ray.direction.dot(n) < 0.0;

@@ -19,7 +19,9 @@ def build():
 
 
 def lib(counters=False):
-    name = "liboracle_counters.so" if counters else "liboracle.so"
+    # counters: False = timing build, True = reference-semantics work counters, "norc" = timing build without the per-hit
+    # material reference count (bench.py's cpu_baseline.no_refcount)
+    name = "liboracle_norc.so" if counters == "norc" else ("liboracle_counters.so" if counters else "liboracle.so")
     if name not in _libs:
         path = os.path.join(BUILD_DIR, name)
         if not os.path.exists(path):
