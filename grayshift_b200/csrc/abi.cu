@@ -245,6 +245,7 @@ int gs_render_accumulate(gs_scene* s, const gs_camera* camera, uint64_t seed, ui
 	if (rc) return rc;
 	if (!d_accum) return fail(GS_ERR_INVALID, "null accumulator");
 	if (sample_count == 0) return GS_OK;
+	if (sample_count > 0x7fffffffu || (uint64_t)sample_begin + sample_count > 0xffffffffull) return fail(GS_ERR_UNSUPPORTED, "sample indices beyond 32 bits");
 	DCamera cam;
 	rc = convert_camera(s, camera, cam);
 	if (rc) return rc;
@@ -275,12 +276,8 @@ int gs_render_adaptive_accumulate(gs_scene* s, const gs_camera* camera, const gs
 	const unsigned total = (unsigned)camera->image_width * (unsigned)camera->image_height;
 	const unsigned n_pixels = pixel_begin >= total ? 0u : (total - pixel_begin + pixel_stride - 1) / pixel_stride;
 	if (n_pixels == 0) return GS_OK;
-	AdaptiveParams ap;
-	ap.confidence_sq = settings->confidence * settings->confidence;  // camera.rs:128-129
-	ap.tolerance_sq = settings->tolerance * settings->tolerance;
-	ap.max_samples = settings->max_samples;
-	ap.n_pixels = n_pixels;
-	ap.accum = static_cast<const float4*>(d_accum);
+	const double confidence_sq = settings->confidence * settings->confidence;  // camera.rs:128-129
+	const double tolerance_sq = settings->tolerance * settings->tolerance;
 	// Camera::sample's loop (camera.rs:135-165) leaves after the first batch that takes `sample_count as u32` past
 	// max_samples: at most max_samples / batch_size + 1 batches.
 	const unsigned long long rounds = (unsigned long long)settings->max_samples / settings->batch_size + 1ull;
@@ -288,54 +285,43 @@ int gs_render_adaptive_accumulate(gs_scene* s, const gs_camera* camera, const gs
 	if (rounds * settings->batch_size > (1ull << 24)) return fail(GS_ERR_UNSUPPORTED, "adaptive sampling beyond 2^24 samples per pixel");
 	rc = begin_entry(s, st);
 	if (rc) return rc;
-	GS_CUDA(s->px_list[0].alloc(n_pixels, st)); GS_CUDA(s->px_list[1].alloc(n_pixels, st));
-	GS_CUDA(s->px_count.alloc(2, st));
+	GS_CUDA(s->px_list[0].alloc((size_t)n_pixels * 2, st));  // the two lists of the rounds, back to back
+	GS_CUDA(s->px_count.alloc(4, st));
 	GS_CUDA(s->lum.alloc(total, st));
 	GS_CUDA(cudaMemsetAsync(s->lum.p, 0, (size_t)total * sizeof(double2), st));
 	GS_CUDA(launch_adaptive_init(s->px_list[0].p, s->px_count.p, pixel_begin, pixel_stride, n_pixels, st));
 	p.seed = seed;
+	p.sample_begin = 0;
 	p.sample_count = settings->batch_size;
-	p.total_items = (unsigned long long)n_pixels * settings->batch_size;  // upper bound; the kernel reads the list length
+	p.total_items = (unsigned long long)n_pixels * settings->batch_size;  // upper bound (sizes the grid); the kernel reads the list lengths
 	p.chunk = 256;
 	p.accum = static_cast<float4*>(d_accum);
 	p.stats = s->stats;
 	p.lum = s->lum.p;
 	p.small_scene = s->small_scene;
 	p.wide = s->wide;
-	for (unsigned long long r = 0; r < rounds; ++r) {
-		const int cur = (int)(r & 1ull), nxt = cur ^ 1;
-		if ((unsigned long long)settings->batch_size * (r + 1ull) > 0xffffffffull) return fail(GS_ERR_UNSUPPORTED, "sample index beyond 32 bits");
-		p.sample_begin = (unsigned)(r * settings->batch_size);
-		p.pixel_list = s->px_list[cur].p;
-		p.n_list = s->px_count.p + cur;
-		p.work_counter = next_counter(s);
-		GS_CUDA(cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned long long), st));
-		GS_CUDA(cudaMemsetAsync(s->px_count.p + nxt, 0, sizeof(unsigned), st));
-		GS_CUDA(launch_render_fixed(p, s->sm_count, false, s->has_triangles, st));
-		GS_CUDA(launch_adaptive_decide(ap, s->px_list[cur].p, s->px_count.p + cur, s->px_list[nxt].p, s->px_count.p + nxt, s->lum.p, st));
-		s->launches += 2;
-		// after batches 1, 2, 4, 8, ... look whether any pixel is still sampling (one 4-byte read): most renders end long
-		// before the cap, and a launch pair that finds an empty list still costs ~10 us
-		if (((r + 1ull) & r) == 0ull && r + 1 < rounds) {
-			unsigned left = 0;
-			GS_CUDA(cudaMemcpyAsync(&left, s->px_count.p + nxt, sizeof left, cudaMemcpyDeviceToHost, st));
-			GS_CUDA(cudaStreamSynchronize(st));
-			if (left == 0) break;
-			if (left <= kAdaptiveTailPixels) {  // a handful of hard pixels: one warp each finishes them in a single launch
-				AdaptiveTailParams tp;
-				tp.sc = s->ds; tp.cam = p.cam; tp.seed = seed;
-				tp.confidence_sq = ap.confidence_sq; tp.tolerance_sq = ap.tolerance_sq;
-				tp.batch_size = settings->batch_size; tp.max_samples = settings->max_samples;
-				tp.list = s->px_list[nxt].p; tp.n_list = s->px_count.p + nxt;
-				tp.accum = static_cast<float4*>(d_accum); tp.lum = s->lum.p;
-				tp.work_counter = next_counter(s); tp.stats = s->stats;
-				GS_CUDA(cudaMemsetAsync(tp.work_counter, 0, sizeof(unsigned long long), st));
-				GS_CUDA(launch_adaptive_tail(tp, left, s->sm_count, s->wide, st));
-				s->launches += 1;
-				break;
-			}
-		}
-	}
+	p.pixel_list = s->px_list[0].p;
+	p.n_list = s->px_count.p;
+	p.work_counter = next_counter(s);
+	p.work_counter2 = next_counter(s);
+	p.confidence_sq = confidence_sq; p.tolerance_sq = tolerance_sq;
+	p.max_samples = settings->max_samples; p.n_pixels = n_pixels;
+	p.tail_pixels = kAdaptiveTailPixels;
+	GS_CUDA(cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned long long), st));
+	GS_CUDA(cudaMemsetAsync(p.work_counter2, 0, sizeof(unsigned long long), st));
+	// every batch round in one cooperative launch (render, grid sync, stop test, grid sync ...) until at most
+	// kAdaptiveTailPixels pixels are left; then one warp per remaining pixel finishes its loop.  No host round trip.
+	GS_CUDA(launch_render_fixed(p, s->sm_count, false, s->has_triangles, st));
+	AdaptiveTailParams tp;
+	tp.sc = s->ds; tp.cam = p.cam; tp.seed = seed;
+	tp.confidence_sq = confidence_sq; tp.tolerance_sq = tolerance_sq;
+	tp.batch_size = settings->batch_size; tp.max_samples = settings->max_samples;
+	tp.lists = s->px_list[0].p; tp.n_list = s->px_count.p; tp.n_pixels = n_pixels;
+	tp.accum = static_cast<float4*>(d_accum); tp.lum = s->lum.p;
+	tp.work_counter = next_counter(s); tp.stats = s->stats;
+	GS_CUDA(cudaMemsetAsync(tp.work_counter, 0, sizeof(unsigned long long), st));
+	GS_CUDA(launch_adaptive_tail(tp, std::min(n_pixels, kAdaptiveTailPixels), s->sm_count, s->wide, st));
+	s->launches += 3;
 	return end_entry(s, st);
 }
 

@@ -285,20 +285,53 @@ __device__ __forceinline__ bool hit_triangle(const DTriangle& tr, const Ray& r, 
 	return true;
 }
 
+// 256-bit read-only loads (sm_100: LDG.E.256).  Every lane walks its own ray, so a load instruction costs the L1 one tag
+// lookup per active lane whatever its width: a 64-byte node in two 32-byte loads instead of four 16-byte ones halves the
+// request rate that binds the traversal once the tree lives in L2 (config 5: L1TEX at 82 % of its peak with 16-byte loads).
+// The pointer must be 32-byte aligned (all records here are 32, 64 or 96 bytes in 256-byte aligned arrays).
+#ifndef GS_LD256
+#define GS_LD256 1  // tuning knob: 0 = 128-bit loads only
+#endif
+__device__ __forceinline__ void ldg256(const void* p, uint4& a, uint4& b) {
+#if defined(__CUDA_ARCH__) && GS_LD256
+	asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+	    : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
+#else
+	a = __ldg(reinterpret_cast<const uint4*>(p)); b = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+#endif
+}
+__device__ __forceinline__ void ldg256(const void* p, float4& a, float4& b) {
+#if defined(__CUDA_ARCH__) && GS_LD256
+	asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+	    : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+#else
+	a = __ldg(reinterpret_cast<const float4*>(p)); b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+#endif
+}
+__device__ __forceinline__ void ldg256(const void* p, double2& a, double2& b) {
+#if defined(__CUDA_ARCH__) && GS_LD256
+	asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a.x), "=d"(a.y), "=d"(b.x), "=d"(b.y) : "l"(p));
+#else
+	a = __ldg(reinterpret_cast<const double2*>(p)); b = __ldg(reinterpret_cast<const double2*>(p) + 1);
+#endif
+}
+
 __device__ __forceinline__ DSphere load_sphere(const DSphere* __restrict__ p, uint32_t i) {
-	const double2* q = reinterpret_cast<const double2*>(p + i);
-	double2 a = __ldg(q), b = __ldg(q + 1);
+	double2 a, b;
+	ldg256(p + i, a, b);
 	return DSphere{a.x, a.y, b.x, b.y};
 }
 __device__ __forceinline__ DQuad load_quad(const DQuad* __restrict__ p, uint32_t i) {
 	const double2* q = reinterpret_cast<const double2*>(p + i);
-	double2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3), e = __ldg(q + 4), f = __ldg(q + 5);
+	double2 a, b, c, d, e, f;
+	ldg256(q, a, b); ldg256(q + 2, c, d); ldg256(q + 4, e, f);
 	return DQuad{a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y, e.x, e.y, f.x, f.y};
 }
 
 __device__ __forceinline__ DTriangle load_triangle(const DTriangle* __restrict__ p, uint32_t i) {
 	const double2* q = reinterpret_cast<const double2*>(p + i);
-	double2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3), e = __ldg(q + 4), f = __ldg(q + 5);
+	double2 a, b, c, d, e, f;
+	ldg256(q, a, b); ldg256(q + 2, c, d); ldg256(q + 4, e, f);
 	return DTriangle{a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y, e.x, e.y, f.x, f.y};
 }
 
@@ -419,9 +452,9 @@ struct Trav2 {
 			const int2 link = *reinterpret_cast<const int2*>(np + 3);
 			link0 = link.x; link1 = link.y;
 		} else {
-			xy0 = __ldg(np); xy1 = __ldg(np + 1); z01 = __ldg(np + 2);
-			const int4 link = __ldg(reinterpret_cast<const int4*>(np + 3));
-			link0 = link.x; link1 = link.y;
+			float4 lk;
+			ldg256(np, xy0, xy1); ldg256(np + 2, z01, lk);
+			link0 = __float_as_int(lk.x); link1 = __float_as_int(lk.y);
 		}
 		if (kCount) ++(*node_visits);
 		float t0 = fmaf(xy0.x, rc.idx, -rc.oix), t1 = fmaf(xy0.y, rc.idx, -rc.oix);
@@ -520,7 +553,8 @@ struct Trav8 {
 		const uint32_t node = base + __popc((grp >> 8) & ((1u << slot) - 1u));
 		if (grp & 0xffu) { stack[sp] = (int)base; stack[sp + 1] = (int)(grp & 0xffffu); sp += 2; }
 		const uint4* np = reinterpret_cast<const uint4*>(sc.nodes8 + node);
-		const uint4 hd = __ldg(np), qx = __ldg(np + 1), qy = __ldg(np + 2), qz = __ldg(np + 3);
+		uint4 hd, qx, qy, qz;
+		ldg256(np, hd, qx); ldg256(np + 2, qy, qz);
 		const uint2 tail = __ldg(reinterpret_cast<const uint2*>(np + 4) + 1);  // child_base, sphere_base: only child_base is used here
 		if (kCount) ++(*node_visits);
 		const float ax = __uint_as_float((hd.w & 0xffu) << 23) * rc.idx;

@@ -2,6 +2,7 @@
 // (validation, re-layout of the flat scene description, the two trees, upload) and multi_gpu.cu.  Not part of the ABI.
 #pragma once
 #include <cstdint>
+#include <memory>
 #include <string>
 #include <thread>
 #include <vector>
@@ -87,7 +88,8 @@ struct gs_scene {
 
 	// ---- host copies kept for (re)building node arrays: re-padding when a camera sits outside the assumed origin range,
 	// and the tree that was not built at creation (gs_scene_set_option "bvh_width")
-	std::vector<gs_bvh_node> h_nodes;
+	std::unique_ptr<gs_bvh_node[]> h_nodes;  // copy of the caller's tree (filled by a helper thread while the layout runs)
+	size_t n_nodes = 0;
 	std::vector<int> h_node_to_dnode;   // ABI node -> DNode index (internal nodes), -1 for leaves
 	std::vector<int> h_leaf_code;       // ABI node -> leaf code (leaves)
 	std::vector<int> h_bfs;             // internal ABI nodes in BFS order (= binary device order)

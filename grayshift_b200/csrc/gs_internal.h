@@ -15,19 +15,16 @@ struct RenderParams {
 	float4* accum;                         // W*H (sum r, sum g, sum b, count)
 	unsigned long long* work_counter;      // dynamic work distribution
 	unsigned long long* stats;             // [0] rays, [1] paths, [2] texel fetches, [3] node visits
-	// adaptive rounds (Camera::sample's batch loop run as one fixed-count launch per batch over the pixels still sampling)
-	const uint32_t* pixel_list;            // work item i belongs to pixel_list[i / sample_count]; nullptr = every pixel
-	const unsigned* n_list;                // device-resident length of pixel_list (total_items is derived from it on the device)
+	// adaptive rounds (Camera::sample's batch loop, camera.rs:135-165, run batch by batch over the pixels still sampling -- all rounds
+	// inside ONE cooperative launch: render phase, grid-wide sync, stop test, grid-wide sync, next round)
+	uint32_t* pixel_list;                  // two lists of n_pixels entries each, back to back: [0] = the pixels of round 0; nullptr = every pixel (fixed count)
+	unsigned* n_list;                      // [0], [1] = lengths of the two lists, [2] = index of the list the rounds leave for the tail kernel
+	unsigned long long* work_counter2;     // a second work counter: rounds alternate between the two
 	double2* lum;                          // per pixel (sum of luminance, sum of its square), camera.rs:132-133,146-147
+	double confidence_sq, tolerance_sq;    // the stop test of camera.rs:150-164
+	unsigned max_samples, n_pixels, tail_pixels;  // n_pixels = capacity of each list; the rounds end once <= tail_pixels pixels are left
 	bool small_scene;                      // nodes + primitives <= kSmallSceneBytes: the launch takes the 6-CTAs-per-SM build
 	bool wide;                             // traverse sc.nodes8 (eight-wide tree) instead of sc.nodes
-};
-
-struct AdaptiveParams {  // the stop test of camera.rs:150-164
-	double confidence_sq, tolerance_sq;
-	unsigned max_samples;
-	unsigned n_pixels;  // pixels this rank started with (upper bound of every list)
-	const float4* accum;
 };
 
 struct AdaptiveTailParams {  // the last few pixels: one warp per pixel runs the rest of its batch loop (adaptive_tail_kernel)
@@ -36,8 +33,9 @@ struct AdaptiveTailParams {  // the last few pixels: one warp per pixel runs the
 	unsigned long long seed;
 	double confidence_sq, tolerance_sq;
 	unsigned batch_size, max_samples;
-	const uint32_t* list;
-	const unsigned* n_list;
+	const uint32_t* lists;     // the two pixel lists of the rounds (n_pixels entries each)
+	const unsigned* n_list;    // [0], [1] their lengths, [2] which of them holds the pixels still sampling
+	unsigned n_pixels;
 	float4* accum;
 	const double2* lum;
 	unsigned long long* work_counter;
@@ -48,8 +46,6 @@ struct AdaptiveTailParams {  // the last few pixels: one warp per pixel runs the
 cudaError_t launch_render_fixed(const RenderParams& p, int sm_count, bool count_nodes, bool triangles, cudaStream_t stream);
 cudaError_t launch_adaptive_init(uint32_t* list, unsigned* n_list, unsigned pixel_begin, unsigned pixel_stride, unsigned n_pixels, cudaStream_t stream);
 cudaError_t launch_adaptive_tail(const AdaptiveTailParams& p, unsigned n_upper, int sm_count, bool wide, cudaStream_t stream);
-cudaError_t launch_adaptive_decide(const AdaptiveParams& p, const uint32_t* list, const unsigned* n_in, uint32_t* next, unsigned* n_out,
-                                   const double2* lum, cudaStream_t stream);
 cudaError_t launch_resolve(const float4* accum, int n_pixels, float* out_rgb, unsigned* out_counts, cudaStream_t stream);
 cudaError_t launch_resolve_rgb8(const float4* accum, int n_pixels, unsigned char* out_rgb8, unsigned* out_counts, cudaStream_t stream);
 cudaError_t launch_camera_rays(const DCamera& cam, unsigned long long seed, unsigned sample, int pixel_begin, int pixel_end, double* rays_out,

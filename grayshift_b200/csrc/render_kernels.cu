@@ -7,10 +7,13 @@
 //   Work items are handed out in chunks through one global 64-bit atomic per warp per chunk.
 //   Each lane keeps (sum r, sum g, sum b, n) for its current pixel in shared memory and flushes with one
 //   128-bit vector reduction (red.global.add.v4.f32) when its pixel changes.
-// adaptive sampling (camera.rs:125-171, exact batch / stop-test semantics, Q3-Q5): one launch of the same megakernel per
-//   batch over the pixels still sampling + adaptive_decide_kernel (the stop test); adaptive_tail_kernel (one warp per
-//   pixel) for the last few pixels.  See below.
+// adaptive sampling (camera.rs:125-171, exact batch / stop-test semantics, Q3-Q5): the same megakernel, launched ONCE
+//   (cooperatively) for all batches: a round renders one batch of every pixel still sampling, a grid-wide sync, the stop
+//   test rebuilds the list, a second sync, next round -- no host round trip; adaptive_tail_kernel (one warp per pixel)
+//   finishes the last few pixels.  See below.
 // Grids are sized to SM count x resident CTAs (persistent), never to the image.
+#include <cooperative_groups.h>
+
 #include "gs_internal.h"
 #include "gs_kernel_util.cuh"
 
@@ -63,7 +66,11 @@ template <int kF>
 __global__ void __launch_bounds__(kBlock, (kF & 8) ? GS_MIN_BLOCKS + 1 : GS_MIN_BLOCKS) render_fixed_kernel(const __grid_constant__ RenderParams P) {
 	constexpr bool kAdaptive = (kF & 4) != 0;
 	using Trav = typename std::conditional<(kF & 16) != 0, Trav8, Trav2>::type;
-	const unsigned long long total_items = kAdaptive ? (unsigned long long)__ldg(P.n_list) * P.sample_count : P.total_items;
+	// adaptive: one iteration of the round loop below per batch; these change from round to round
+	unsigned long long total_items = kAdaptive ? (unsigned long long)__ldcg(P.n_list) * P.sample_count : P.total_items;
+	unsigned round = 0;
+	const uint32_t* pixel_list = P.pixel_list;
+	unsigned long long* work_counter = P.work_counter;
 	__shared__ uint8_t s_perm[256];
 	__shared__ float4 s_top[kTopNodes > 0 ? kTopNodes * 4 : 1];
 	if (kTopNodes > 0)
@@ -86,10 +93,10 @@ __global__ void __launch_bounds__(kBlock, (kF & 8) ? GS_MIN_BLOCKS + 1 : GS_MIN_
 	__shared__ float s_sum[4][kBlock];
 	__shared__ double s_lum[kAdaptive ? 2 : 1][kAdaptive ? kBlock : 1];  // adaptive: the lane's share of sum, sq_sum (f64 like the reference)
 	__shared__ uint32_t s_pix[kBlock];
-	__shared__ unsigned long long s_chunk[kBlock / 32][3];
+	__shared__ unsigned long long s_chunk[kBlock / 32][4];  // next item, end of the chunk, "no more chunks", (pixel << 32 | sample) of the next item
 	unsigned long long* const chunk = s_chunk[threadIdx.x >> 5];
 	s_pix[threadIdx.x] = 0xffffffffu;
-	if (lane == 0) { chunk[0] = 0ull; chunk[1] = 0ull; chunk[2] = 0ull; }
+	if (lane == 0) { chunk[0] = 0ull; chunk[1] = 0ull; chunk[2] = 0ull; chunk[3] = 0ull; }
 	__syncwarp();
 
 	auto flush_pixel = [&]() {
@@ -119,6 +126,7 @@ __global__ void __launch_bounds__(kBlock, (kF & 8) ? GS_MIN_BLOCKS + 1 : GS_MIN_
 		state = kDead;
 	};
 
+	for (;;) {  // rounds of the adaptive sampler (the fixed-count kernels leave after the first)
 	for (;;) {
 		// ---- phase A1: shade the lanes whose traversal finished --------------------------------------
 		if (state == kShade) {
@@ -136,29 +144,43 @@ __global__ void __launch_bounds__(kBlock, (kF & 8) ? GS_MIN_BLOCKS + 1 : GS_MIN_
 			unsigned long long warp_next = chunk[0], warp_end = chunk[1];
 			bool exhausted = chunk[2] != 0ull;
 			if (!(exhausted && warp_next >= warp_end)) {
+				// item = pixel * sample_count + sample.  The 64-bit division runs once per CHUNK (warp-uniform); within a chunk
+				// the (pixel, sample) of the next item is carried along and a lane adds its rank with one 32-bit division
+				// (sample_count <= 2^31, checked by the ABI) -- the per-lane 64-bit div/mod pair was ~150 instructions at
+				// seven active lanes.
+				uint32_t pixel0 = (uint32_t)(chunk[3] >> 32), sample0 = (uint32_t)chunk[3];
 				if (warp_next >= warp_end) {
 					unsigned long long base = 0;
-					if (lane == 0) base = atomicAdd(P.work_counter, (unsigned long long)P.chunk);
+					if (lane == 0) base = atomicAdd(work_counter, (unsigned long long)P.chunk);
 					base = __shfl_sync(kFull, base, 0);
 					if (base >= total_items) exhausted = true;
-					else { warp_next = base; warp_end = min(base + (unsigned long long)P.chunk, total_items); }
+					else {
+						warp_next = base; warp_end = min(base + (unsigned long long)P.chunk, total_items);
+						pixel0 = (uint32_t)(base / P.sample_count);
+						sample0 = (uint32_t)(base - (unsigned long long)pixel0 * P.sample_count);
+					}
 				}
 				const unsigned long long avail = warp_end - warp_next;
 				if (state == kDead) {
 					const unsigned rank = __popc(dead & lt_mask);
 					if (rank < avail) {
-						const unsigned long long item = warp_next + rank;
-						uint32_t pixel = (uint32_t)(item / P.sample_count);
-						const uint32_t sample = (uint32_t)(item % P.sample_count) + P.sample_begin;
-						if (kAdaptive) pixel = __ldg(P.pixel_list + pixel);
+						const uint32_t off = sample0 + rank, q = off / P.sample_count;
+						uint32_t pixel = pixel0 + q;
+						const uint32_t sample = off - q * P.sample_count + (kAdaptive ? round * P.sample_count : P.sample_begin);
+						if (kAdaptive) pixel = __ldcg(pixel_list + pixel);  // the lists are rewritten every round: read them past the (incoherent) L1
 						path_begin(st, P.cam, P.seed, pixel, sample);
 						state = kSetup;
 					}
 				}
 				const unsigned long long need = (unsigned long long)__popc(dead);
-				warp_next += need < avail ? need : avail;
+				const uint32_t adv = (uint32_t)(need < avail ? need : avail);
+				warp_next += adv;
+				{
+					const uint32_t off = sample0 + adv, q = off / P.sample_count;
+					pixel0 += q; sample0 = off - q * P.sample_count;
+				}
 				__syncwarp();
-				if (lane == 0) { chunk[0] = warp_next; chunk[1] = warp_end; chunk[2] = exhausted ? 1ull : 0ull; }
+				if (lane == 0) { chunk[0] = warp_next; chunk[1] = warp_end; chunk[2] = exhausted ? 1ull : 0ull; chunk[3] = ((unsigned long long)pixel0 << 32) | sample0; }
 				__syncwarp();
 			}
 		}
@@ -249,9 +271,65 @@ __global__ void __launch_bounds__(kBlock, (kF & 8) ? GS_MIN_BLOCKS + 1 : GS_MIN_
 #endif
 	}
 	flush_pixel();
-	// every work item starts exactly one path: no per-lane counter for them
+	if (!kAdaptive) {
+		if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(P.stats + 1, total_items);  // every work item starts exactly one path
+		break;
+	}
+	// ---- between two batches: Camera::sample's stop test (camera.rs:150-164) for every pixel of this round's list ----
+	// (the whole grid is co-resident: cooperative launch, persistent CTAs)
+	const unsigned cur = round & 1u, nxt = cur ^ 1u;
+	s_pix[threadIdx.x] = 0xffffffffu;
+	if (lane == 0) { chunk[0] = 0ull; chunk[1] = 0ull; chunk[2] = 0ull; chunk[3] = 0ull; }
+	__threadfence();
+	cooperative_groups::this_grid().sync();
+	{
+		const unsigned n = __ldcg(P.n_list + cur);
+		uint32_t* const next = P.pixel_list + (size_t)nxt * P.n_pixels;
+		for (unsigned base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += gridDim.x * blockDim.x) {
+			const unsigned k = base + lane;
+			bool more = false;
+			uint32_t pixel = 0;
+			if (k < n) {
+				pixel = __ldcg(pixel_list + k);
+				const double sample_count = (double)__ldcg(&P.accum[pixel].w);  // exact: one 1.0f per path, far below 2^24
+				const double2 sl = __ldcg(P.lum + pixel);
+				const double mean = sl.x / sample_count;  // camera.rs:150-158
+				const double variance_sq = 1.0 / (sample_count - 1.0) * (sl.y - sl.x * sl.x / sample_count);
+				const double convergence_sq = P.confidence_sq * variance_sq / sample_count;
+				const bool converged = convergence_sq < mean * mean * P.tolerance_sq;
+				const unsigned sc_u32 = sample_count >= 4294967295.0 ? 4294967295u : (unsigned)sample_count;
+				more = !converged && !(sc_u32 > P.max_samples);  // camera.rs:162-164
+			}
+			const unsigned m = __ballot_sync(kFull, more);  // one atomic per warp; the order of the list does not matter
+			if (m) {
+				unsigned slot = 0;
+				if (lane == 0) slot = atomicAdd(P.n_list + nxt, (unsigned)__popc(m));
+				slot = __shfl_sync(kFull, slot, 0);
+				if (more) next[slot + __popc(m & ((1u << lane) - 1u))] = pixel;
+			}
+		}
+		if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(P.stats + 1, (unsigned long long)n * P.sample_count);
+	}
+	__threadfence();
+	cooperative_groups::this_grid().sync();
+	const unsigned left = __ldcg(P.n_list + nxt);
+	if (left <= P.tail_pixels) {  // the last few pixels (or none): adaptive_tail_kernel takes list `nxt`
+		if (blockIdx.x == 0 && threadIdx.x == 0) P.n_list[2] = nxt;
+		break;
+	}
+	// next round: the other list, the other work counter; this round's are reset for the round after
+	++round;
+	pixel_list = P.pixel_list + (size_t)nxt * P.n_pixels;
+	total_items = (unsigned long long)left * P.sample_count;
+	work_counter = (round & 1u) ? P.work_counter2 : P.work_counter;
+	if (blockIdx.x == 0 && threadIdx.x == 0) {
+		P.n_list[cur] = 0u;  // becomes the output list of the coming round's stop test; nobody reads it before the next grid sync
+		*((round & 1u) ? P.work_counter : P.work_counter2) = 0ull;  // last used a round ago
+	}
+	state = kDead;
+	tv.park();
+	}
 	flush_stats(P.stats, pc, 0u);
-	if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(P.stats + 1, total_items);
 }
 
 // ---- the adaptive sampler's control flow, camera.rs:125-171 ------------------------------------------------------
@@ -264,37 +342,7 @@ __global__ void adaptive_init_kernel(uint32_t* __restrict__ list, unsigned* __re
                                      unsigned n_pixels) {
 	const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
 	if (k < n_pixels) list[k] = pixel_begin + k * pixel_stride;
-	if (k == 0) { n_list[0] = n_pixels; n_list[1] = 0u; }
-}
-
-__global__ void adaptive_decide_kernel(const uint32_t* __restrict__ list, const unsigned* __restrict__ n_in, uint32_t* __restrict__ next,
-                                       unsigned* __restrict__ n_out, const float4* __restrict__ accum, const double2* __restrict__ lum,
-                                       double confidence_sq, double tolerance_sq, unsigned max_samples) {
-	const unsigned n = *n_in;
-	const unsigned lane = threadIdx.x & 31u;
-	for (unsigned base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += gridDim.x * blockDim.x) {
-		const unsigned k = base + lane;
-		bool more = false;
-		uint32_t pixel = 0;
-		if (k < n) {
-			pixel = list[k];
-			const double sample_count = (double)accum[pixel].w;  // exact: one 1.0f per path, far below 2^24
-			const double2 s = lum[pixel];
-			const double mean = s.x / sample_count;  // camera.rs:150-158
-			const double variance_sq = 1.0 / (sample_count - 1.0) * (s.y - s.x * s.x / sample_count);
-			const double convergence_sq = confidence_sq * variance_sq / sample_count;
-			const bool converged = convergence_sq < mean * mean * tolerance_sq;
-			const unsigned sc_u32 = sample_count >= 4294967295.0 ? 4294967295u : (unsigned)sample_count;
-			more = !converged && !(sc_u32 > max_samples);  // camera.rs:162-164
-		}
-		const unsigned m = __ballot_sync(kFull, more);  // one atomic per warp; the order of the list does not matter
-		if (m) {
-			unsigned slot = 0;
-			if (lane == 0) slot = atomicAdd(n_out, (unsigned)__popc(m));
-			slot = __shfl_sync(kFull, slot, 0);
-			if (more) next[slot + __popc(m & ((1u << lane) - 1u))] = pixel;
-		}
-	}
+	if (k == 0) { n_list[0] = n_pixels; n_list[1] = 0u; n_list[2] = 0u; }
 }
 
 // The tail of an adaptive render: when only a few pixels are still sampling, a launch per batch costs more than it
@@ -313,7 +361,9 @@ __global__ void __launch_bounds__(kBlock) adaptive_tail_kernel(const __grid_cons
 	load_perm(s_perm, P.sc.perlin_perm);
 	const unsigned lane = threadIdx.x & 31u;
 	const unsigned lt_mask = (1u << lane) - 1u;
-	const unsigned n_list = __ldg(P.n_list);
+	const unsigned which = P.n_list[2] & 1u;
+	const unsigned n_list = P.n_list[which];
+	const uint32_t* const list = P.lists + (size_t)which * P.n_pixels;
 	PathCounters pc = {0u, 0u, 0u};
 	unsigned paths = 0;
 	for (;;) {
@@ -321,7 +371,7 @@ __global__ void __launch_bounds__(kBlock) adaptive_tail_kernel(const __grid_cons
 		if (lane == 0) k = atomicAdd(P.work_counter, 1ull);
 		k = __shfl_sync(kFull, k, 0);
 		if (k >= n_list) break;
-		const uint32_t pixel = P.list[k];
+		const uint32_t pixel = list[k];
 		const float4 a0 = P.accum[pixel];
 		const double2 l0 = P.lum[pixel];
 		double sum = 0.0, sq_sum = 0.0, cr = 0.0, cg = 0.0, cb = 0.0;  // this lane's share of what is added now
@@ -480,8 +530,13 @@ cudaError_t launch_render_fixed(const RenderParams& p, int sm_count, bool count_
 	unsigned long long blocks_needed = (warps_needed + (kBlock / 32) - 1) / (kBlock / 32);
 	unsigned long long grid = (unsigned long long)sm_count * per_sm;  // persistent: SMs x resident CTAs
 	if (blocks_needed < grid) grid = blocks_needed ? blocks_needed : 1;
+	// the adaptive variants run every batch round in this one launch and synchronise the grid in between: cooperative launch
+	// (all CTAs co-resident -- the grid is sized to the occupancy anyway)
+	void* args[] = {const_cast<RenderParams*>(&p)};
 	switch (variant) {
-#define X(v) case v: render_fixed_kernel<v><<<(unsigned)grid, kBlock, 0, stream>>>(p); break;
+#define X(v) case v: \
+		if ((v) & 4) return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(&render_fixed_kernel<v>), dim3((unsigned)grid), dim3(kBlock), args, 0, stream); \
+		render_fixed_kernel<v><<<(unsigned)grid, kBlock, 0, stream>>>(p); break;
 		GS_FIXED_VARIANTS(X)
 #undef X
 		default: return cudaErrorInvalidValue;
@@ -504,14 +559,6 @@ cudaError_t launch_adaptive_tail(const AdaptiveTailParams& p, unsigned n_upper, 
 	if (blocks_needed < grid) grid = blocks_needed ? blocks_needed : 1;
 	if (wide) adaptive_tail_kernel<18><<<(unsigned)grid, kBlock, 0, stream>>>(p);
 	else adaptive_tail_kernel<2><<<(unsigned)grid, kBlock, 0, stream>>>(p);
-	return cudaGetLastError();
-}
-
-cudaError_t launch_adaptive_decide(const AdaptiveParams& p, const uint32_t* list, const unsigned* n_in, uint32_t* next, unsigned* n_out,
-                                   const double2* lum, cudaStream_t stream) {
-	const unsigned blocks = (p.n_pixels + 255) / 256;
-	adaptive_decide_kernel<<<blocks < 1184u ? (blocks ? blocks : 1u) : 1184u, 256, 0, stream>>>(list, n_in, next, n_out, p.accum, lum, p.confidence_sq,
-	                                                                                          p.tolerance_sq, p.max_samples);
 	return cudaGetLastError();
 }
 

@@ -295,11 +295,8 @@ void build_wide_topology(const gs_bvh_node* N, size_t n_nodes, WideBuild& w) {
 		area[i] = (float)(dx * dy + dy * dz + dz * dx);
 	});
 	auto internal = [&](int a) { return N[a].ref_count == 0; };
-	std::vector<int> level;  // depth of each wide node
-	w.of_bin.push_back(0);
-	level.push_back(1);
-	for (size_t h = 0; h < w.of_bin.size(); ++h) {
-		const int a = w.of_bin[h];
+	// one wide node: collapse + octant slots; returns the number of internal kids
+	auto make_node = [&](int a, int* slot_kid) -> int {
 		int kids[8] = {N[a].left, N[a].right, -1, -1, -1, -1, -1, -1};
 		int n = 2;
 		while (n < 8) {
@@ -311,7 +308,6 @@ void build_wide_topology(const gs_bvh_node* N, size_t n_nodes, WideBuild& w) {
 			kids[best] = N[c].left;
 			kids[n++] = N[c].right;
 		}
-		// octant slots
 		double centre[3];
 		for (int x = 0; x < 3; ++x) centre[x] = 0.5 * (N[a].bounds_min[x] + N[a].bounds_max[x]);
 		double score[8][8];
@@ -320,7 +316,7 @@ void build_wide_topology(const gs_bvh_node* N, size_t n_nodes, WideBuild& w) {
 			for (int x = 0; x < 3; ++x) rel[x] = 0.5 * (N[kids[k]].bounds_min[x] + N[kids[k]].bounds_max[x]) - centre[x];
 			for (int s = 0; s < 8; ++s) score[k][s] = ((s & 1) ? rel[0] : -rel[0]) + ((s & 2) ? rel[1] : -rel[1]) + ((s & 4) ? rel[2] : -rel[2]);
 		}
-		int slot_kid[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
+		for (int s = 0; s < 8; ++s) slot_kid[s] = -1;
 		bool placed[8] = {false, false, false, false, false, false, false, false};
 		for (int round = 0; round < n; ++round) {
 			int bk = -1, bs = -1;
@@ -332,17 +328,33 @@ void build_wide_topology(const gs_bvh_node* N, size_t n_nodes, WideBuild& w) {
 			slot_kid[bs] = kids[bk];
 			placed[bk] = true;
 		}
-		int first_child = -1;
-		for (int s = 0; s < 8; ++s) {
-			w.kids.push_back(slot_kid[s]);
-			if (slot_kid[s] >= 0 && internal(slot_kid[s])) {
-				if (first_child < 0) first_child = (int)w.of_bin.size();
-				w.of_bin.push_back(slot_kid[s]);
-				level.push_back(level[h] + 1);
-			}
-		}
-		w.child_base.push_back(first_child < 0 ? 0 : first_child);
-		w.depth = std::max(w.depth, level[h]);
+		int n_int = 0;
+		for (int s = 0; s < 8; ++s) if (slot_kid[s] >= 0 && internal(slot_kid[s])) ++n_int;
+		return n_int;
+	};
+	// level by level: the nodes of a level are independent of each other (host threads), their internal kids -- in node
+	// order, then slot order -- are the next level: the same numbering a breadth-first queue gives
+	std::vector<int> level{0}, next, n_int;
+	size_t base = 0;
+	while (!level.empty()) {
+		const size_t L = level.size();
+		w.kids.resize((base + L) * 8);
+		w.child_base.resize(base + L);
+		w.of_bin.insert(w.of_bin.end(), level.begin(), level.end());
+		n_int.assign(L, 0);
+		parallel_for(L, [&](size_t i) { n_int[i] = make_node(level[i], w.kids.data() + (base + i) * 8); }, 2048);
+		size_t total = 0;
+		for (size_t i = 0; i < L; ++i) { w.child_base[base + i] = n_int[i] ? (int)(base + L + total) : 0; total += (size_t)n_int[i]; }
+		next.assign(total, 0);
+		parallel_for(L, [&](size_t i) {
+			if (!n_int[i]) return;
+			int* out = next.data() + ((size_t)w.child_base[base + i] - (base + L));
+			const int* kid = w.kids.data() + (base + i) * 8;
+			for (int s = 0; s < 8; ++s) if (kid[s] >= 0 && internal(kid[s])) *out++ = kid[s];
+		}, 2048);
+		base += L;
+		level.swap(next);
+		++w.depth;
 	}
 }
 }  // namespace
@@ -352,16 +364,22 @@ int layout_scene(gs_scene* s, const gs_scene_desc* d) {
 	Lap lap("gs_scene_create");
 	const size_t nN = d->n_nodes;
 	const gs_bvh_node* N = d->nodes;
-	// host copy of the tree (kept for re-padding and for the tree not built now)
-	s->h_nodes.resize(nN);
+	// host copy of the tree (kept for re-padding and for the tree not built now): uninitialised storage, filled by helper
+	// threads while this thread goes on with the caller's array (128 MB for 10^6 primitives: first-touch page faults dominate)
+	s->h_nodes.reset(new gs_bvh_node[nN]);
+	s->n_nodes = nN;
+	std::vector<std::thread> copiers;
 	{
-		const size_t chunk = 1u << 14;
-		parallel_for((nN + chunk - 1) / chunk, [&](size_t c) {
-			const size_t lo = c * chunk, hi = std::min(nN, lo + chunk);
-			std::memcpy(s->h_nodes.data() + lo, N + lo, (hi - lo) * sizeof(gs_bvh_node));
-		}, 8);
+		const unsigned T = std::max(1u, std::min(4u, host_threads() / 4));
+		const size_t chunk = (nN + T - 1) / T;
+		gs_bvh_node* dst = s->h_nodes.get();
+		for (unsigned t = 0; t < T; ++t) {
+			const size_t lo = (size_t)t * chunk, hi = std::min(nN, lo + chunk);
+			if (lo < hi) copiers.emplace_back([=] { std::memcpy(dst + lo, N + lo, (hi - lo) * sizeof(gs_bvh_node)); });
+		}
 	}
-	lap("copy nodes");
+	struct Join { std::vector<std::thread>& t; ~Join() { for (auto& x : t) if (x.joinable()) x.join(); } } join_copiers{copiers};
+	lap("copy nodes (started)");
 	// tree check: children carry larger indices than their parent, so one ascending sweep sees every parent first
 	{
 		std::vector<int8_t> depth(nN, -1);
@@ -422,8 +440,105 @@ int layout_scene(gs_scene* s, const gs_scene_desc* d) {
 			if (fresh && kind != kKindMovingSphere) s->h_leaf_direct[leaf] = (int)idx;
 		}
 	};
+	// Does every primitive sit in exactly one leaf?  (True for any tree without spatial splits.)  Then the order below can be
+	// computed from subtree sizes and filled by all host threads; otherwise the serial walk with its "seen before" test.
+	bool unique_refs = !root_leaf && d->n_prim_refs == d->n_spheres + d->n_quads + d->n_triangles;
+	if (unique_refs) {
+		std::vector<std::atomic<uint8_t>> seen_s(d->n_spheres), seen_q(d->n_quads), seen_t(d->n_triangles);
+		std::atomic<bool> dup{false};
+		parallel_for(d->n_prim_refs, [&](size_t i) {
+			const uint32_t r = d->prim_refs[i], kind = r >> 30, idx = r & kRefIndexMask;
+			std::atomic<uint8_t>& f = kind == 0 ? seen_s[idx] : (kind == 1 ? seen_q[idx] : seen_t[idx]);
+			if (f.exchange(1, std::memory_order_relaxed)) dup = true;
+		});
+		unique_refs = !dup.load();
+	}
 	if (root_leaf) emit_leaf(0);
-	else {
+	else if (unique_refs) {
+		// per wide node: primitives (per kind) and references of its own leaf kids, singles and larger leaves apart
+		struct Own { uint32_t single[3], multi[3], refs_single, refs_multi; };
+		std::vector<Own> own(nW);
+		parallel_for(nW, [&](size_t h) {
+			Own o{};
+			const int* kids = wb.kids.data() + 8 * h;
+			for (int k = 0; k < 8; ++k) {
+				const int c = kids[k];
+				if (c < 0 || N[c].ref_count == 0) continue;
+				for (int j = 0; j < N[c].ref_count; ++j) {
+					const uint32_t kind = d->prim_refs[N[c].first_ref + j] >> 30;
+					if (N[c].ref_count == 1) ++o.single[kind]; else ++o.multi[kind];
+				}
+				if (N[c].ref_count == 1) ++o.refs_single; else o.refs_multi += (uint32_t)N[c].ref_count;
+			}
+			own[h] = o;
+		}, 4096);
+		// subtree totals bottom-up (kids carry larger indices), then start offsets top-down in the walk's order:
+		// own singles, own larger leaves, then the internal kids' subtrees in slot order
+		struct Tot { uint32_t prim[3], refs; };
+		std::vector<Tot> sub(nW), start(nW);
+		for (size_t h = nW; h-- > 0;) {
+			Tot t{{own[h].single[0] + own[h].multi[0], own[h].single[1] + own[h].multi[1], own[h].single[2] + own[h].multi[2]}, own[h].refs_single + own[h].refs_multi};
+			const int* kids = wb.kids.data() + 8 * h;
+			int rank = 0;
+			for (int k = 0; k < 8; ++k) {
+				if (kids[k] < 0 || N[kids[k]].ref_count != 0) continue;
+				const Tot& c = sub[(size_t)wb.child_base[h] + rank++];
+				for (int x = 0; x < 3; ++x) t.prim[x] += c.prim[x];
+				t.refs += c.refs;
+			}
+			sub[h] = t;
+		}
+		start[0] = Tot{{0, 0, 0}, 0};
+		for (size_t h = 0; h < nW; ++h) {
+			Tot cur = start[h];
+			for (int x = 0; x < 3; ++x) cur.prim[x] += own[h].single[x] + own[h].multi[x];
+			cur.refs += own[h].refs_single + own[h].refs_multi;
+			const int* kids = wb.kids.data() + 8 * h;
+			int rank = 0;
+			for (int k = 0; k < 8; ++k) {
+				if (kids[k] < 0 || N[kids[k]].ref_count != 0) continue;
+				const size_t c = (size_t)wb.child_base[h] + rank++;
+				start[c] = cur;
+				for (int x = 0; x < 3; ++x) cur.prim[x] += sub[c].prim[x];
+				cur.refs += sub[c].refs;
+			}
+		}
+		sph_src.assign(d->n_spheres, 0); quad_src.assign(d->n_quads, 0); tri_src.assign(d->n_triangles, 0);
+		refs.assign(d->n_prim_refs, 0u);
+		std::atomic<bool> moving_seen{false};
+		parallel_for(nW, [&](size_t h) {
+			uint32_t next_prim[3] = {start[h].prim[0], start[h].prim[1], start[h].prim[2]};
+			uint32_t next_ref = start[h].refs;
+			for (int x = 0; x < 3; ++x) s->w_prim_base[3 * h + x] = next_prim[x];
+			const int* kids = wb.kids.data() + 8 * h;
+			for (int pass = 0; pass < 2; ++pass)
+				for (int k = 0; k < 8; ++k) {
+					const int c = kids[k];
+					if (c < 0 || N[c].ref_count == 0 || (N[c].ref_count == 1) != (pass == 0)) continue;
+					const uint32_t first = next_ref;
+					uint32_t last_ref = 0;
+					for (int j = 0; j < N[c].ref_count; ++j) {
+						const uint32_t r = d->prim_refs[N[c].first_ref + j], kind = r >> 30, idx = r & kRefIndexMask;
+						const uint32_t dev = next_prim[kind]++;
+						uint32_t dkind = kind;
+						if (kind == 0) {
+							sph_src[dev] = (int)idx;
+							if (d->spheres[idx].moving) { dkind = kKindMovingSphere; moving_seen = true; }
+						} else if (kind == 1) quad_src[dev] = (int)idx;
+						else tri_src[dev] = (int)idx;
+						last_ref = (dkind << kRefKindShift) | dev;
+						refs[next_ref++] = last_ref;
+					}
+					s->h_leaf_code[c] = leaf_code(first, (uint32_t)N[c].ref_count);
+					if (N[c].ref_count == 1) {
+						const uint32_t kind = last_ref >> kRefKindShift, idx = last_ref & kRefIndexMask;
+						s->h_leaf_code[c] = leaf_code((kind << 25) | idx, 0u);
+						if (kind != kKindMovingSphere) s->h_leaf_direct[c] = (int)idx;
+					}
+				}
+		}, 4096);
+		any_moving = moving_seen.load();
+	} else {
 		std::vector<int> stack{0};
 		while (!stack.empty()) {
 			const int h = stack.back(); stack.pop_back();
@@ -646,11 +761,11 @@ static int upload_nodes(gs_scene* s, void** dev, size_t bytes, const Staging& st
 
 int build_nodes2(gs_scene* s, double origin_limit) {
 	Lap lap("build_nodes2");
-	const std::vector<gs_bvh_node>& N = s->h_nodes;
+	const gs_bvh_node* N = s->h_nodes.get();
 	if (s->h_bfs.empty() && N[0].ref_count == 0) {  // breadth-first numbering of the internal nodes = device order (top levels contiguous)
-		s->h_node_to_dnode.assign(N.size(), -1);
+		s->h_node_to_dnode.assign(s->n_nodes, -1);
 		std::vector<int>& queue = s->h_bfs;
-		queue.reserve(N.size() / 2 + 1);
+		queue.reserve(s->n_nodes / 2 + 1);
 		queue.push_back(0);
 		for (size_t h = 0; h < queue.size(); ++h) {
 			const int n = queue[h];
@@ -694,7 +809,7 @@ int build_nodes2(gs_scene* s, double origin_limit) {
 
 int build_nodes8(gs_scene* s, double origin_limit) {
 	Lap lap("build_nodes8");
-	const std::vector<gs_bvh_node>& N = s->h_nodes;
+	const gs_bvh_node* N = s->h_nodes.get();
 	const size_t nW = s->w_child_base.size();
 	if (nW == 0) return fail(GS_ERR_UNSUPPORTED, "the eight-wide tree needs an internal root");
 	if (s->wide_depth + 1 > kMaxStack8) return fail(GS_ERR_UNSUPPORTED, "eight-wide tree deeper than its traversal stack");
@@ -713,7 +828,7 @@ int build_nodes8(gs_scene* s, double origin_limit) {
 	GS_CUDA(staging_acquire(node_bytes + link_bytes, stg));
 	struct StageGuard { Staging& g; cudaEvent_t ev = nullptr; ~StageGuard() { staging_release(g, ev); } } guard{stg};
 	DNode8* out = reinterpret_cast<DNode8*>(stg.p);
-	int* links = reinterpret_cast<int*>(stg.p + node_bytes);
+	int* links = any_link ? reinterpret_cast<int*>(stg.p + node_bytes) : nullptr;  // no side table without a leaf that needs one
 	std::atomic<int> bad{0};
 	parallel_for(nW, [&](size_t h) {
 		const int* kids = s->w_kids.data() + 8 * h;

@@ -12,6 +12,7 @@
 template <class T> static inline T __ldg(const T* p) { return *p; }
 static inline float __uint_as_float(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }
 static inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
+static inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }
 static inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
 static inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {
 	const uint64_t both = ((uint64_t)y << 32) | x;
