@@ -268,6 +268,24 @@ impl Scene {
         Ok(stats)
     }
 
+    /// Camera::render on several GPUs in one call (gs_render_multi): `scenes[g]` lives on device g.
+    pub fn render_multi(scenes: &[Scene], camera: &gs_camera, settings: &gs_sample_settings, seed: u64, rgb: &mut [f32],
+                        counts: Option<&mut [u32]>) -> std::io::Result<gs_stats> {
+        let n = (camera.image_width as usize) * (camera.image_height as usize);
+        assert!(!scenes.is_empty() && rgb.len() >= n * 3);
+        let raws: Vec<*mut gs_scene> = scenes.iter().map(|s| s.raw).collect();
+        let counts_ptr = match counts {
+            Some(c) => {
+                assert!(c.len() >= n);
+                c.as_mut_ptr()
+            }
+            None => std::ptr::null_mut(),
+        };
+        let mut stats = gs_stats::default();
+        check(unsafe { gs_render_multi(raws.as_ptr(), raws.len() as c_int, camera, settings, seed, rgb.as_mut_ptr(), counts_ptr, &mut stats) })?;
+        Ok(stats)
+    }
+
     pub fn trace_closest(&self, rays: &[f64], tmin: f64, tmax: f64) -> std::io::Result<(Vec<i32>, Vec<f64>)> {
         let n = rays.len() / 7;
         let (mut ids, mut t) = (vec![0i32; n], vec![0f64; n]);

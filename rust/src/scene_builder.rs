@@ -11,7 +11,7 @@
 //!   impl Hittable for RotateY      { fn flatten(..) { self.object.flatten(&xf.rotated_y(self.sin_theta, self.cos_theta), out) } }
 //!   impl Hittable for ConstantMedium { fn flatten(..) { out.begin_medium(xf); self.boundary.flatten(xf, out);
 //!                                                        out.end_medium(1.0 / -self.density_neg_inv, &self.phase_function) } }
-use crate::ffi::*;
+use crate::camera::ffi::*;
 use std::collections::HashMap;
 
 /// p -> R p + t with R a rotation about y: R = [[c,0,s],[0,1,0],[-s,0,c]] (hittable.rs:195-199).

@@ -98,3 +98,47 @@ def test_rust_scene_builder_covers_every_primitive_kind_of_the_abi():
     body = body[:body.index("}\n    }")]
     for f in desc_fields:
         assert re.search(rf"\b{f}:", body), f"FlatScene::desc() does not set gs_scene_desc.{f}"
+
+
+# the scene-building API main.rs compiles against: module path -> constructors / methods that must exist
+RUST_API = {
+    "camera.rs": ["pub fn new(", "pub fn render(&self, world: Box<dyn Hittable>, image_file: &mut File) -> std::io::Result<()>", "pub struct SampleSettings",
+                  "pub enum Background", "pub struct HDRI", "pub image: radiant::Image", "pub rotation: Vec3"],
+    "hittable/hittable.rs": ["pub trait Hittable: Send + Sync", "fn flatten(&self, xf: &Xform, out: &mut SceneBuilder)", "pub fn add(&mut self, object: Box<dyn Hittable>)",
+                             "pub fn clear(&mut self)", "impl Hittable for HittableList", "impl Hittable for Translate", "impl Hittable for RotateY",
+                             "pub fn new(object: Box<dyn Hittable>, offset: Vec3)", "pub fn new(object: Box<dyn Hittable>, angle: f64)"],
+    "hittable/BVH.rs": ["pub fn from_list(list: HittableList) -> Box<Self>", "pub fn construct_tree(", "impl Hittable for BVHNode"],
+    "hittable/sphere.rs": ["pub fn new_stationary(center: Vec3, radius: f64, material: Arc<dyn Material>)", "pub fn new_moving(center1: Vec3, center2: Vec3, radius: f64, material: Arc<dyn Material>)"],
+    "hittable/quad.rs": ["pub fn new(q: Vec3, u: Vec3, v: Vec3, material: Arc<dyn Material>)", "pub fn cube(point_a: Vec3, point_b: Vec3, material: Arc<dyn Material>) -> HittableList"],
+    "hittable/triangle.rs": ["pub fn new(a: Vec3, b: Vec3, c: Vec3, material: Arc<dyn Material>)"],
+    "hittable/volume.rs": ["pub fn new(boundary: Box<dyn Hittable>, density: f64, phase_function: Arc<dyn Material>)", "pub fn from_isotropic_color(boundary: Box<dyn Hittable>, density: f64, color: Vec3)"],
+    "material.rs": ["pub trait Material: Send + Sync", "pub fn from_color(albedo: Vec3)", "pub fn from_texture(texture: Arc<dyn Texture>)", "pub fn new(albedo: Vec3, fuzz: f64)",
+                    "pub fn new(refraction_index: f64)", "pub fn reflectance(cosine: f64, refraction_index: f64) -> f64", "impl Material for DiffuseLight", "impl Material for Isotropic"],
+    "texture.rs": ["pub trait Texture: Send + Sync", "pub fn from_rgb(red: f64, green: f64, blue: f64)", "pub fn from_colors(scale: f64, even_color: Vec3, odd_color: Vec3)",
+                   "pub fn new<P: AsRef<Path>>(filepath: P) -> Result<Self, ImageError>", "pub fn new(scale: f64)"],
+    "util/vec3.rs": ["pub const ZERO: Vec3", "pub const fn new(x: f64, y: f64, z: f64)", "impl Mul<Vec3> for Vec3"],
+    "util/util.rs": ["pub fn random_f64(min: f64, max: f64) -> f64", "pub fn random_vector(min: f64, max: f64) -> Vec3"],
+    "color.rs": ["pub fn write_color", "pub fn luminance"],
+    "AABB.rs": ["pub fn from_corners(a: Vec3, b: Vec3)", "pub fn longest_axis(&self) -> usize"],
+    "ray.rs": ["pub struct Ray"], "ONB.rs": ["pub struct OrthonormalBasis"], "hittable/mod.rs": ["pub mod BVH;", "pub mod volume;"], "util/mod.rs": ["pub mod vec3;"],
+}
+
+
+def test_rust_shell_provides_the_scene_building_api_of_main_rs():
+    """every module main.rs declares (mod color; mod ray; mod hittable; mod camera; mod util; mod material; mod AABB; mod texture;
+    mod ONB;) exists under rust/src with the constructors and signatures main.rs:61-888 calls, so that dropping the reference's
+    main.rs next to them is the only step left (uncompiled here: no Rust toolchain)"""
+    src = os.path.join(ROOT, "rust", "src")
+    for rel, needles in RUST_API.items():
+        path = os.path.join(src, rel)
+        assert os.path.exists(path), f"rust/src/{rel} is missing"
+        text = re.sub(r"\s+", " ", open(path).read())
+        for n in needles:
+            assert re.sub(r"\s+", " ", n) in text, f"rust/src/{rel} lacks `{n}`"
+    # every hittable / material / texture type flattens itself
+    for rel, n in (("hittable/sphere.rs", 1), ("hittable/quad.rs", 1), ("hittable/triangle.rs", 1), ("hittable/volume.rs", 1), ("hittable/BVH.rs", 1),
+                   ("hittable/hittable.rs", 4), ("material.rs", 6), ("texture.rs", 5)):
+        assert open(os.path.join(src, rel)).read().count("fn flatten(") >= n, f"rust/src/{rel}: flatten() impls missing"
+    cam = open(os.path.join(src, "camera.rs")).read()
+    for call in ("world.flatten(", "builder.finish(", "ffi::Scene::create(", "render_multi(", "write_color("):
+        assert call in cam, f"Camera::render lacks {call}"
