@@ -306,7 +306,8 @@ int gs_render_adaptive_accumulate(gs_scene* s, const gs_camera* camera, const gs
 	p.work_counter2 = next_counter(s);
 	p.confidence_sq = confidence_sq; p.tolerance_sq = tolerance_sq;
 	p.max_samples = settings->max_samples; p.n_pixels = n_pixels;
-	p.tail_pixels = kAdaptiveTailPixels;
+	static const unsigned tail_pixels = [] { const char* e = std::getenv("GS_TAIL_PIXELS"); return e ? (unsigned)std::atoi(e) : kAdaptiveTailPixels; }();  // tuning knob
+	p.tail_pixels = tail_pixels;
 	GS_CUDA(cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned long long), st));
 	GS_CUDA(cudaMemsetAsync(p.work_counter2, 0, sizeof(unsigned long long), st));
 	// every batch round in one cooperative launch (render, grid sync, stop test, grid sync ...) until at most
@@ -320,7 +321,7 @@ int gs_render_adaptive_accumulate(gs_scene* s, const gs_camera* camera, const gs
 	tp.accum = static_cast<float4*>(d_accum); tp.lum = s->lum.p;
 	tp.work_counter = next_counter(s); tp.stats = s->stats;
 	GS_CUDA(cudaMemsetAsync(tp.work_counter, 0, sizeof(unsigned long long), st));
-	GS_CUDA(launch_adaptive_tail(tp, std::min(n_pixels, kAdaptiveTailPixels), s->sm_count, s->wide, st));
+	GS_CUDA(launch_adaptive_tail(tp, std::min(n_pixels, tail_pixels), s->sm_count, s->wide, st));
 	s->launches += 3;
 	return end_entry(s, st);
 }

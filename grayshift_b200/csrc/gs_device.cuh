@@ -29,10 +29,13 @@ namespace gs {
 // ------------------------------------------------------------------------------------------
 // Records
 // ------------------------------------------------------------------------------------------
+#ifndef GS_NODE_CH
+#define GS_NODE_CH 1  // binary node boxes as (centre, half extent) instead of (min, max); see Trav2::node_step
+#endif
 struct __align__(16) DNode {
-	float4 xy0;  // child 0: min.x, max.x, min.y, max.y
+	float4 xy0;  // child 0: min.x, max.x, min.y, max.y      (GS_NODE_CH: centre.x, half.x, centre.y, half.y)
 	float4 xy1;  // child 1
-	float4 z01;  // c0.min.z, c0.max.z, c1.min.z, c1.max.z
+	float4 z01;  // c0.min.z, c0.max.z, c1.min.z, c1.max.z   (GS_NODE_CH: c0 centre.z, half.z, c1 centre.z, half.z)
 	int4 link;   // child0, child1 (>= 0 internal node index; < 0 leaf code), unused, unused
 };
 // Eight-wide compressed node (large scenes: config 5's 10^6 spheres, whose binary nodes come from L2).  96 bytes:
@@ -289,49 +292,65 @@ __device__ __forceinline__ bool hit_triangle(const DTriangle& tr, const Ray& r, 
 // lookup per active lane whatever its width: a 64-byte node in two 32-byte loads instead of four 16-byte ones halves the
 // request rate that binds the traversal once the tree lives in L2 (config 5: L1TEX at 82 % of its peak with 16-byte loads).
 // The pointer must be 32-byte aligned (all records here are 32, 64 or 96 bytes in 256-byte aligned arrays).
+// Measured (profiles/r02_variants.log): +3...4 % on the 10^6-sphere scene, -3 % on the L1-resident final scene (the 8-register
+// alignment of the destination costs the register-bound kernel a few spills), hence kWide: the kernels of the eight-wide tree
+// -- the large scenes -- use them, the binary-tree kernels keep 128-bit loads.
 #ifndef GS_LD256
-#define GS_LD256 1  // tuning knob: 0 = 128-bit loads only
+#define GS_LD256 1  // tuning knob: 0 = 128-bit loads only, 1 = 256-bit loads in the eight-wide kernels, 2 = everywhere
 #endif
+template <bool kWide> struct Ld256 { static constexpr bool on = GS_LD256 == 2 || (GS_LD256 == 1 && kWide); };
+template <bool kOn>
 __device__ __forceinline__ void ldg256(const void* p, uint4& a, uint4& b) {
-#if defined(__CUDA_ARCH__) && GS_LD256
-	asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-	    : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
-#else
+#if defined(__CUDA_ARCH__)
+	if (kOn) {
+		asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+		    : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
+		return;
+	}
+#endif
 	a = __ldg(reinterpret_cast<const uint4*>(p)); b = __ldg(reinterpret_cast<const uint4*>(p) + 1);
-#endif
 }
+template <bool kOn>
 __device__ __forceinline__ void ldg256(const void* p, float4& a, float4& b) {
-#if defined(__CUDA_ARCH__) && GS_LD256
-	asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-	    : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
-#else
+#if defined(__CUDA_ARCH__)
+	if (kOn) {
+		asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+		    : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+		return;
+	}
+#endif
 	a = __ldg(reinterpret_cast<const float4*>(p)); b = __ldg(reinterpret_cast<const float4*>(p) + 1);
-#endif
 }
+template <bool kOn>
 __device__ __forceinline__ void ldg256(const void* p, double2& a, double2& b) {
-#if defined(__CUDA_ARCH__) && GS_LD256
-	asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a.x), "=d"(a.y), "=d"(b.x), "=d"(b.y) : "l"(p));
-#else
-	a = __ldg(reinterpret_cast<const double2*>(p)); b = __ldg(reinterpret_cast<const double2*>(p) + 1);
+#if defined(__CUDA_ARCH__)
+	if (kOn) {
+		asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a.x), "=d"(a.y), "=d"(b.x), "=d"(b.y) : "l"(p));
+		return;
+	}
 #endif
+	a = __ldg(reinterpret_cast<const double2*>(p)); b = __ldg(reinterpret_cast<const double2*>(p) + 1);
 }
 
+template <bool kWide = false>
 __device__ __forceinline__ DSphere load_sphere(const DSphere* __restrict__ p, uint32_t i) {
 	double2 a, b;
-	ldg256(p + i, a, b);
+	ldg256<Ld256<kWide>::on>(p + i, a, b);
 	return DSphere{a.x, a.y, b.x, b.y};
 }
+template <bool kWide = false>
 __device__ __forceinline__ DQuad load_quad(const DQuad* __restrict__ p, uint32_t i) {
 	const double2* q = reinterpret_cast<const double2*>(p + i);
 	double2 a, b, c, d, e, f;
-	ldg256(q, a, b); ldg256(q + 2, c, d); ldg256(q + 4, e, f);
+	ldg256<Ld256<kWide>::on>(q, a, b); ldg256<Ld256<kWide>::on>(q + 2, c, d); ldg256<Ld256<kWide>::on>(q + 4, e, f);
 	return DQuad{a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y, e.x, e.y, f.x, f.y};
 }
 
+template <bool kWide = false>
 __device__ __forceinline__ DTriangle load_triangle(const DTriangle* __restrict__ p, uint32_t i) {
 	const double2* q = reinterpret_cast<const double2*>(p + i);
 	double2 a, b, c, d, e, f;
-	ldg256(q, a, b); ldg256(q + 2, c, d); ldg256(q + 4, e, f);
+	ldg256<Ld256<kWide>::on>(q, a, b); ldg256<Ld256<kWide>::on>(q + 2, c, d); ldg256<Ld256<kWide>::on>(q + 4, e, f);
 	return DTriangle{a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y, e.x, e.y, f.x, f.y};
 }
 
@@ -356,6 +375,25 @@ __device__ __forceinline__ float safe_rcp(float d) {
 #define GS_NODE_LOAD 1  // tuning knob: 1 = branch-free child selection (the link load is issued together with the box loads)
 #endif
 
+// The traversal stack of one thread.  Its first kSmem entries may live in shared memory, laid out [entry][thread] (no bank
+// conflicts: a warp's lanes hit 32 consecutive words whatever their stack depths are... per entry), the rest in the per-thread
+// local array (the round-1 profile: the all-local stack made up 30 % of the kernel's L1 traffic at 1.8 useful bytes per
+// 32-byte sector).  kSmem = 0: local memory only (the parity and per-path kernels).
+template <int kSmem, int kStride>
+struct StackT {
+	int* local;
+	int* smem;  // &s_stack[0][thread]; entry i at smem[i * kStride]
+	__device__ __forceinline__ int get(int i) const {
+		if (kSmem > 0 && i < kSmem) return smem[i * kStride];
+		return local[kSmem > 0 ? i - kSmem : i];
+	}
+	__device__ __forceinline__ void set(int i, int v) const {
+		if (kSmem > 0 && i < kSmem) smem[i * kStride] = v;
+		else local[kSmem > 0 ? i - kSmem : i] = v;
+	}
+};
+using LocalStack = StackT<0, 1>;
+
 struct RayConsts {  // per-ray values derived from the Ray; recomputed whenever a traversal is (re)entered
 	float idx, idy, idz;     // 1 / direction
 	float oix, oiy, oiz;     // origin * (1 / direction): slab distance = fma(plane, id, -oi)
@@ -375,7 +413,7 @@ __device__ __forceinline__ RayConsts ray_consts(const Ray& r, double t_closest) 
 // One leaf: HittableList::hit over its primitives (hittable.rs:70-86) with the reference's interval rules.
 // `leaf` is a leaf code.  kTris = the scene holds triangles (kernels for scenes without any are
 // instantiated without the triangle branch: it costs registers and instruction-cache space in the hot loop).
-template <bool kTris>
+template <bool kTris, bool kWide = false>
 __device__ __forceinline__ void leaf_intersect(const DeviceScene& sc, const Ray& r, RayConsts& rc, double tmin, Hit& best, int leaf) {
 	const uint32_t code = (uint32_t)(-1 - leaf);
 	uint32_t first = code >> 4, count = code & 15u;
@@ -388,11 +426,11 @@ __device__ __forceinline__ void leaf_intersect(const DeviceScene& sc, const Ray&
 		const uint32_t index = ref & kRefIndexMask;
 		const uint32_t kind = ref >> kRefKindShift;
 		if (kTris && kind == kKindTriangle) {
-			const DTriangle tr = load_triangle(sc.tris, index);
+			const DTriangle tr = load_triangle<kWide>(sc.tris, index);
 			double t, u, v;
 			if (hit_triangle(tr, r, tmin, best.t, t, u, v)) { best.t = t; best.ref = ref; best.u = (float)u; best.v = (float)v; }
 		} else if (kind == kKindQuad) {
-			const DQuad q = load_quad(sc.quads, index);
+			const DQuad q = load_quad<kWide>(sc.quads, index);
 			double t, al, be;
 			if (hit_quad(q, r, tmin, best.t, t, al, be)) {
 				// exact tie between two quads: the one the reference visits later wins (t <= closest, plane.rs:27)
@@ -404,7 +442,7 @@ __device__ __forceinline__ void leaf_intersect(const DeviceScene& sc, const Ray&
 				if (accept) { best.t = t; best.ref = ref; }
 			}
 		} else {  // sphere, stationary (kind 0) or moving (kind 3)
-			const DSphere s = load_sphere(sc.spheres, index);
+			const DSphere s = load_sphere<kWide>(sc.spheres, index);
 			// |d|^2 (Vec3::length_squared, sphere.rs:71) and its reciprocal are recomputed per test: eleven f64
 			// instructions, against four registers held through the whole traversal of a register-bound kernel
 			const double a = r.dx * r.dx + r.dy * r.dy + r.dz * r.dz, inv_a = f64_rcp(a);
@@ -424,8 +462,9 @@ struct Trav2 {
 	int sp;     // stack entries in use
 	Hit best;
 
-	__device__ __forceinline__ void init(const DeviceScene& sc, const Ray&, int* stack, double tmax) {
-		stack[0] = kStackSentinel;
+	template <class Stack>
+	__device__ __forceinline__ void init(const DeviceScene& sc, const Ray&, const Stack& stack, double tmax) {
+		stack.set(0, kStackSentinel);
 		sp = 1;
 		node = sc.root;
 		best.t = tmax; best.ref = kNoHit; best.u = 0.f; best.v = 0.f;
@@ -441,8 +480,8 @@ struct Trav2 {
 	// (scene_layout.cu build_nodes): conservative, never culls a true hit.  Precondition: wants_node().
 	// kTop > 0: the first kTop nodes (breadth-first order = the top levels of the tree) are read from the CTA's
 	// shared-memory copy `top`; one generic-address load serves both cases, so lanes do not diverge on it.
-	template <bool kCount, int kTop>
-	__device__ __forceinline__ void node_step(const DeviceScene& sc, const RayConsts& rc, int* stack, uint32_t* node_visits, const float4* top) {
+	template <bool kCount, int kTop, class Stack>
+	__device__ __forceinline__ void node_step(const DeviceScene& sc, const RayConsts& rc, const Stack& stack, uint32_t* node_visits, const float4* top) {
 		const float4* np = reinterpret_cast<const float4*>(sc.nodes + node);
 		float4 xy0, xy1, z01;
 		int link0, link1;
@@ -453,10 +492,33 @@ struct Trav2 {
 			link0 = link.x; link1 = link.y;
 		} else {
 			float4 lk;
-			ldg256(np, xy0, xy1); ldg256(np + 2, z01, lk);
+			ldg256<Ld256<false>::on>(np, xy0, xy1); ldg256<Ld256<false>::on>(np + 2, z01, lk);
 			link0 = __float_as_int(lk.x); link1 = __float_as_int(lk.y);
 		}
 		if (kCount) ++(*node_visits);
+#if GS_NODE_CH
+		// Boxes as (centre, half extent): the slab interval of an axis is tm -+ half * |1/d| around tm = (centre - o) / d --
+		// three FMAs (the |.| and the sign are operand modifiers), where (min, max) planes cost two FMAs plus a min and a max.
+		// The ALU pipe (min / max / compare / select) is the busier one in this loop: six fewer instructions per node and
+		// twelve moved to the FMA pipe.  Same conservative padding as the (min, max) form.
+		float tm, th;
+		tm = fmaf(xy0.x, rc.idx, -rc.oix); th = xy0.y * fabsf(rc.idx);
+		const float nx0 = tm - th, fx0 = tm + th;
+		tm = fmaf(xy0.z, rc.idy, -rc.oiy); th = xy0.w * fabsf(rc.idy);
+		const float ny0 = tm - th, fy0 = tm + th;
+		tm = fmaf(z01.x, rc.idz, -rc.oiz); th = z01.y * fabsf(rc.idz);
+		const float nz0 = tm - th, fz0 = tm + th;
+		const float en0 = fmaxf(fmaxf(nx0, ny0), fmaxf(nz0, 0.0f));
+		const float ex0 = fminf(fminf(fx0, fy0), fminf(fz0, rc.tmax32));
+		tm = fmaf(xy1.x, rc.idx, -rc.oix); th = xy1.y * fabsf(rc.idx);
+		const float nx1 = tm - th, fx1 = tm + th;
+		tm = fmaf(xy1.z, rc.idy, -rc.oiy); th = xy1.w * fabsf(rc.idy);
+		const float ny1 = tm - th, fy1 = tm + th;
+		tm = fmaf(z01.z, rc.idz, -rc.oiz); th = z01.w * fabsf(rc.idz);
+		const float nz1 = tm - th, fz1 = tm + th;
+		const float en1 = fmaxf(fmaxf(nx1, ny1), fmaxf(nz1, 0.0f));
+		const float ex1 = fminf(fminf(fx1, fy1), fminf(fz1, rc.tmax32));
+#else
 		float t0 = fmaf(xy0.x, rc.idx, -rc.oix), t1 = fmaf(xy0.y, rc.idx, -rc.oix);
 		float t2 = fmaf(xy0.z, rc.idy, -rc.oiy), t3 = fmaf(xy0.w, rc.idy, -rc.oiy);
 		float t4 = fmaf(z01.x, rc.idz, -rc.oiz), t5 = fmaf(z01.y, rc.idz, -rc.oiz);
@@ -467,6 +529,7 @@ struct Trav2 {
 		t4 = fmaf(z01.z, rc.idz, -rc.oiz); t5 = fmaf(z01.w, rc.idz, -rc.oiz);
 		const float en1 = fmaxf(fmaxf(fminf(t0, t1), fminf(t2, t3)), fmaxf(fminf(t4, t5), 0.0f));
 		const float ex1 = fminf(fminf(fmaxf(t0, t1), fmaxf(t2, t3)), fminf(fmaxf(t4, t5), rc.tmax32));
+#endif
 		const bool h0 = en0 <= ex0, h1 = en1 <= ex1;
 #if GS_NODE_LOAD == 1
 		// Select form: both links are consumed unconditionally, so their load is issued with the box loads.  (In the
@@ -474,16 +537,16 @@ struct Trav2 {
 		// dependent L1 round trips.)
 		const bool first0 = h0 && (!h1 || !(en1 < en0));
 		const int first = first0 ? link0 : link1, second = first0 ? link1 : link0;
-		if (h0 && h1) stack[sp++] = second;
+		if (h0 && h1) stack.set(sp++, second);
 		if (h0 || h1) node = first;
-		else node = stack[--sp];
+		else node = stack.get(--sp);
 #else
-		if (!h0 && !h1) { node = stack[--sp]; }
+		if (!h0 && !h1) { node = stack.get(--sp); }
 		else {
 			int near = link0, far = link1;
 			if (h0 && h1) {
 				if (en1 < en0) { int tmp = near; near = far; far = tmp; }
-				stack[sp++] = far;
+				stack.set(sp++, far);
 				node = near;
 			} else node = h0 ? near : far;
 		}
@@ -491,10 +554,10 @@ struct Trav2 {
 	}
 
 	// The leaf under `node`, then pop.  Precondition: wants_leaf().
-	template <bool kTris>
-	__device__ __forceinline__ void leaf_step(const DeviceScene& sc, const Ray& r, RayConsts& rc, double tmin, int* stack) {
+	template <bool kTris, class Stack>
+	__device__ __forceinline__ void leaf_step(const DeviceScene& sc, const Ray& r, RayConsts& rc, double tmin, const Stack& stack) {
 		leaf_intersect<kTris>(sc, r, rc, tmin, best, node);
-		node = stack[--sp];
+		node = stack.get(--sp);
 	}
 };
 
@@ -517,7 +580,8 @@ struct Trav8 {
 		return ((__float_as_uint(x) >> 31) | ((__float_as_uint(y) >> 31) << 1) | ((__float_as_uint(z) >> 31) << 2)) ^ 7u;
 	}
 	__device__ __forceinline__ static uint32_t octinv_of(const RayConsts& rc) { return octinv_bits(rc.idx, rc.idy, rc.idz); }
-	__device__ __forceinline__ void init(const DeviceScene&, const Ray& r, int*, double tmax) {
+	template <class Stack>
+	__device__ __forceinline__ void init(const DeviceScene&, const Ray& r, const Stack&, double tmax) {
 		// a group holding only the root: base 0, imask bit 0, hit bit of slot 0
 		base = 0u; grp = (1u << 8) | (1u << octinv_bits((float)r.dx, (float)r.dy, (float)r.dz)); leaf_node = 0u; sp = 0;
 		best.t = tmax; best.ref = kNoHit; best.u = 0.f; best.v = 0.f;
@@ -528,9 +592,10 @@ struct Trav8 {
 	__device__ __forceinline__ bool wants_node() const { return (grp & 0x00ff00ffu) != 0u && (grp & 0x00ff0000u) == 0u; }
 	__device__ __forceinline__ uint32_t pending_leaf_kind() const { return 0u; }
 
-	__device__ __forceinline__ void refill(const int* stack) {  // nothing left in the current group: continue with the enclosing one
+	template <class Stack>
+	__device__ __forceinline__ void refill(const Stack& stack) {  // nothing left in the current group: continue with the enclosing one
 		if ((grp & 0x00ff00ffu) == 0u) {
-			if (sp > 0) { sp -= 2; base = (uint32_t)stack[sp]; grp = (uint32_t)stack[sp + 1]; }
+			if (sp > 0) { sp -= 2; base = (uint32_t)stack.get(sp); grp = (uint32_t)stack.get(sp + 1); }
 			else grp = 0u;
 		}
 	}
@@ -544,17 +609,17 @@ struct Trav8 {
 	// hits the new current group (the rest of the old one goes on the stack).  Precondition: wants_node().
 	// Slab distances: plane = corner + q * step, so t = q * (step / d) + (corner - o) / d; with q taken as (32768 + q) the
 	// constant absorbs -32768 * step / d (its rounding error, 2^-9 of a grid step, is covered by the builder's margin).
-	template <bool kCount, int kTop>
-	__device__ __forceinline__ void node_step(const DeviceScene& sc, const RayConsts& rc, int* stack, uint32_t* node_visits, const float4*) {
+	template <bool kCount, int kTop, class Stack>
+	__device__ __forceinline__ void node_step(const DeviceScene& sc, const RayConsts& rc, const Stack& stack, uint32_t* node_visits, const float4*) {
 		const uint32_t octinv = octinv_of(rc);
 		const uint32_t pos = 31u - __clz(grp & 0xffu);
 		grp &= ~(1u << pos);
 		const uint32_t slot = pos ^ octinv;
 		const uint32_t node = base + __popc((grp >> 8) & ((1u << slot) - 1u));
-		if (grp & 0xffu) { stack[sp] = (int)base; stack[sp + 1] = (int)(grp & 0xffffu); sp += 2; }
+		if (grp & 0xffu) { stack.set(sp, (int)base); stack.set(sp + 1, (int)(grp & 0xffffu)); sp += 2; }
 		const uint4* np = reinterpret_cast<const uint4*>(sc.nodes8 + node);
 		uint4 hd, qx, qy, qz;
-		ldg256(np, hd, qx); ldg256(np + 2, qy, qz);
+		ldg256<Ld256<true>::on>(np, hd, qx); ldg256<Ld256<true>::on>(np + 2, qy, qz);
 		const uint2 tail = __ldg(reinterpret_cast<const uint2*>(np + 4) + 1);  // child_base, sphere_base: only child_base is used here
 		if (kCount) ++(*node_visits);
 		const float ax = __uint_as_float((hd.w & 0xffu) << 23) * rc.idx;
@@ -589,8 +654,8 @@ struct Trav8 {
 	}
 
 	// The pending leaf children of `leaf_node`, nearest first.  Precondition: wants_leaf().
-	template <bool kTris>
-	__device__ __forceinline__ void leaf_step(const DeviceScene& sc, const Ray& r, RayConsts& rc, double tmin, int* stack) {
+	template <bool kTris, class Stack>
+	__device__ __forceinline__ void leaf_step(const DeviceScene& sc, const Ray& r, RayConsts& rc, double tmin, const Stack& stack) {
 		const uint32_t octinv = octinv_of(rc);
 		const uint4 c4 = __ldg(reinterpret_cast<const uint4*>(sc.nodes8 + leaf_node) + 4);  // meta[0], meta[1], child_base, sphere_base
 		uint32_t pending = (grp >> 16) & 0xffu;
@@ -608,7 +673,7 @@ struct Trav8 {
 				const uint2 c5 = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint4*>(sc.nodes8 + leaf_node) + 5));  // quad_base, tri_base
 				code = leaf_code((kind << 25) | ((kind == kKindQuad ? c5.x : c5.y) + off), 0u);
 			}
-			leaf_intersect<kTris>(sc, r, rc, tmin, best, code);
+			leaf_intersect<kTris, true>(sc, r, rc, tmin, best, code);
 		}
 		refill(stack);
 	}
@@ -625,8 +690,8 @@ struct Trav8 {
 //
 // One round of the classic while-while traversal: descend to the next leaf, intersect it.
 // Precondition: !tv.done().  kF: bit 0 = count node visits, bit 1 = scene holds triangles.
-template <int kF, int kTop, class Trav>
-__device__ __forceinline__ void trav_round(const DeviceScene& sc, const Ray& r, RayConsts& rc, double tmin, Trav& tv, int* stack,
+template <int kF, int kTop, class Trav, class Stack>
+__device__ __forceinline__ void trav_round(const DeviceScene& sc, const Ray& r, RayConsts& rc, double tmin, Trav& tv, const Stack& stack,
                                            uint32_t* node_visits, const float4* top = nullptr) {
 	while (tv.wants_node()) tv.template node_step<(kF & 1) != 0, kTop>(sc, rc, stack, node_visits, top);
 	if (tv.wants_leaf()) tv.template leaf_step<(kF & 2) != 0>(sc, r, rc, tmin, stack);
@@ -637,13 +702,15 @@ template <int kF>
 __device__ __forceinline__ Hit trace_closest(const DeviceScene& sc, const Ray& r, double tmin, double tmax, uint32_t* node_visits = nullptr) {
 	RayConsts rc = ray_consts(r, tmax);
 	if (kF & 16) {
-		int stack[Trav8::kStackWords];
+		int stack_mem[Trav8::kStackWords];
+		const LocalStack stack{stack_mem, nullptr};
 		Trav8 tv;
 		tv.init(sc, r, stack, tmax);
 		while (!tv.done()) trav_round<kF, 0>(sc, r, rc, tmin, tv, stack, node_visits);
 		return tv.best;
 	} else {
-		int stack[Trav2::kStackWords];
+		int stack_mem[Trav2::kStackWords];
+		const LocalStack stack{stack_mem, nullptr};
 		Trav2 tv;
 		tv.init(sc, r, stack, tmax);
 		while (!tv.done()) trav_round<kF, 0>(sc, r, rc, tmin, tv, stack, node_visits);

@@ -53,6 +53,10 @@ static_assert(kTopNodes <= kNodePad, "gs_scene_create pads the node array to kNo
 #ifndef GS_BAIL
 #define GS_BAIL 6         // resumable traversal: the node loop of a round ends once no more than this many lanes still descend
 #endif
+#ifndef GS_SMEM_STACK
+#define GS_SMEM_STACK 0   // entries of the traversal stack kept in shared memory ([entry][thread]); the rest stays in local memory
+#endif
+constexpr int kSmemStack = GS_SMEM_STACK;
 constexpr int kMinShade = GS_MIN_SHADE;
 constexpr int kBail = GS_BAIL;
 
@@ -66,11 +70,13 @@ template <int kF>
 __global__ void __launch_bounds__(kBlock, (kF & 8) ? GS_MIN_BLOCKS + 1 : GS_MIN_BLOCKS) render_fixed_kernel(const __grid_constant__ RenderParams P) {
 	constexpr bool kAdaptive = (kF & 4) != 0;
 	using Trav = typename std::conditional<(kF & 16) != 0, Trav8, Trav2>::type;
-	// adaptive: one iteration of the round loop below per batch; these change from round to round
-	unsigned long long total_items = kAdaptive ? (unsigned long long)__ldcg(P.n_list) * P.sample_count : P.total_items;
-	unsigned round = 0;
-	const uint32_t* pixel_list = P.pixel_list;
-	unsigned long long* work_counter = P.work_counter;
+	// adaptive: one iteration of the round loop below per batch.  What changes from round to round is CTA-uniform and lives in
+	// shared memory -- as registers these seven values spilled the traversal loop (-27 % on the final scene)
+	__shared__ struct { unsigned long long total_items; const uint32_t* pixel_list; unsigned long long* work_counter; unsigned round; } s_rnd;
+	if (kAdaptive && threadIdx.x == 0) {
+		s_rnd.total_items = (unsigned long long)__ldcg(P.n_list) * P.sample_count;
+		s_rnd.pixel_list = P.pixel_list; s_rnd.work_counter = P.work_counter; s_rnd.round = 0u;
+	}
 	__shared__ uint8_t s_perm[256];
 	__shared__ float4 s_top[kTopNodes > 0 ? kTopNodes * 4 : 1];
 	if (kTopNodes > 0)
@@ -84,7 +90,9 @@ __global__ void __launch_bounds__(kBlock, (kF & 8) ? GS_MIN_BLOCKS + 1 : GS_MIN_
 	Trav tv;
 	tv.park();
 	int seg_medium = -1;
-	int stack[Trav::kStackWords];
+	int stack_mem[Trav::kStackWords - kSmemStack > 0 ? Trav::kStackWords - kSmemStack : 1];
+	__shared__ int s_stack[kSmemStack > 0 ? kSmemStack : 1][kBlock];
+	const StackT<kSmemStack, kBlock> stack{stack_mem, &s_stack[0][threadIdx.x]};
 	// The kernel is register-bound (96 registers = 20 warps per SM), so what is touched once per PATH lives in shared
 	// memory instead of in registers held through every traversal: the lane's running sum for its current pixel
 	// (float4 + pixel id, [field][thread]: conflict-free) and the warp's current chunk of work items [next, end) with
@@ -151,8 +159,9 @@ __global__ void __launch_bounds__(kBlock, (kF & 8) ? GS_MIN_BLOCKS + 1 : GS_MIN_
 				uint32_t pixel0 = (uint32_t)(chunk[3] >> 32), sample0 = (uint32_t)chunk[3];
 				if (warp_next >= warp_end) {
 					unsigned long long base = 0;
-					if (lane == 0) base = atomicAdd(work_counter, (unsigned long long)P.chunk);
+					if (lane == 0) base = atomicAdd(kAdaptive ? s_rnd.work_counter : P.work_counter, (unsigned long long)P.chunk);
 					base = __shfl_sync(kFull, base, 0);
+					const unsigned long long total_items = kAdaptive ? s_rnd.total_items : P.total_items;
 					if (base >= total_items) exhausted = true;
 					else {
 						warp_next = base; warp_end = min(base + (unsigned long long)P.chunk, total_items);
@@ -166,8 +175,8 @@ __global__ void __launch_bounds__(kBlock, (kF & 8) ? GS_MIN_BLOCKS + 1 : GS_MIN_
 					if (rank < avail) {
 						const uint32_t off = sample0 + rank, q = off / P.sample_count;
 						uint32_t pixel = pixel0 + q;
-						const uint32_t sample = off - q * P.sample_count + (kAdaptive ? round * P.sample_count : P.sample_begin);
-						if (kAdaptive) pixel = __ldcg(pixel_list + pixel);  // the lists are rewritten every round: read them past the (incoherent) L1
+						const uint32_t sample = off - q * P.sample_count + (kAdaptive ? s_rnd.round * P.sample_count : P.sample_begin);
+						if (kAdaptive) pixel = __ldcg(s_rnd.pixel_list + pixel);  // the lists are rewritten every round: read them past the (incoherent) L1
 						path_begin(st, P.cam, P.seed, pixel, sample);
 						state = kSetup;
 					}
@@ -272,12 +281,13 @@ __global__ void __launch_bounds__(kBlock, (kF & 8) ? GS_MIN_BLOCKS + 1 : GS_MIN_
 	}
 	flush_pixel();
 	if (!kAdaptive) {
-		if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(P.stats + 1, total_items);  // every work item starts exactly one path
+		if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(P.stats + 1, P.total_items);  // every work item starts exactly one path
 		break;
 	}
 	// ---- between two batches: Camera::sample's stop test (camera.rs:150-164) for every pixel of this round's list ----
 	// (the whole grid is co-resident: cooperative launch, persistent CTAs)
-	const unsigned cur = round & 1u, nxt = cur ^ 1u;
+	const unsigned cur = s_rnd.round & 1u, nxt = cur ^ 1u;
+	const uint32_t* const pixel_list = s_rnd.pixel_list;
 	s_pix[threadIdx.x] = 0xffffffffu;
 	if (lane == 0) { chunk[0] = 0ull; chunk[1] = 0ull; chunk[2] = 0ull; chunk[3] = 0ull; }
 	__threadfence();
@@ -318,14 +328,19 @@ __global__ void __launch_bounds__(kBlock, (kF & 8) ? GS_MIN_BLOCKS + 1 : GS_MIN_
 		break;
 	}
 	// next round: the other list, the other work counter; this round's are reset for the round after
-	++round;
-	pixel_list = P.pixel_list + (size_t)nxt * P.n_pixels;
-	total_items = (unsigned long long)left * P.sample_count;
-	work_counter = (round & 1u) ? P.work_counter2 : P.work_counter;
-	if (blockIdx.x == 0 && threadIdx.x == 0) {
-		P.n_list[cur] = 0u;  // becomes the output list of the coming round's stop test; nobody reads it before the next grid sync
-		*((round & 1u) ? P.work_counter : P.work_counter2) = 0ull;  // last used a round ago
+	__syncthreads();  // everybody has read this round's s_rnd
+	if (threadIdx.x == 0) {
+		const unsigned round = s_rnd.round + 1u;
+		s_rnd.round = round;
+		s_rnd.pixel_list = P.pixel_list + (size_t)nxt * P.n_pixels;
+		s_rnd.total_items = (unsigned long long)left * P.sample_count;
+		s_rnd.work_counter = (round & 1u) ? P.work_counter2 : P.work_counter;
+		if (blockIdx.x == 0) {
+			P.n_list[cur] = 0u;  // becomes the output list of the coming round's stop test; nobody reads it before the next grid sync
+			*((round & 1u) ? P.work_counter : P.work_counter2) = 0ull;  // last used a round ago
+		}
 	}
+	__syncthreads();
 	state = kDead;
 	tv.park();
 	}

@@ -782,7 +782,16 @@ int build_nodes2(gs_scene* s, double origin_limit) {
 	DNode* out = reinterpret_cast<DNode*>(stg.p);
 	auto child_box = [&](int abi, float* mnmx) {
 		const gs_bvh_node& c = N[abi];
-		for (int a = 0; a < 3; ++a) { mnmx[a * 2] = float_down(c.bounds_min[a] - pad); mnmx[a * 2 + 1] = float_up(c.bounds_max[a] + pad); }
+		for (int a = 0; a < 3; ++a) {
+			const double lo = c.bounds_min[a] - pad, hi = c.bounds_max[a] + pad;
+#if GS_NODE_CH
+			// (centre, half extent): [centre - half, centre + half] covers the padded box
+			const float centre = (float)(0.5 * (lo + hi));
+			mnmx[a * 2] = centre; mnmx[a * 2 + 1] = float_up(std::fmax(hi - (double)centre, (double)centre - lo));
+#else
+			mnmx[a * 2] = float_down(lo); mnmx[a * 2 + 1] = float_up(hi);
+#endif
+		}
 	};
 	auto link = [&](int abi) { return s->h_node_to_dnode[abi] >= 0 ? s->h_node_to_dnode[abi] : s->h_leaf_code[abi]; };
 	parallel_for(s->h_bfs.size(), [&](size_t k) {

@@ -70,7 +70,8 @@ __global__ void __launch_bounds__(kBlock) wf_traverse_kernel(const __grid_consta
 	Trav2 tv;  // the wavefront pipeline walks the binary tree
 	RayConsts rc;
 	int medium = -1;
-	int stack[kMaxStack];
+	int stack_mem[kMaxStack];
+	const LocalStack stack{stack_mem, nullptr};
 	PathCounters pc = {0u, 0u, 0u};
 	bool drained = false;
 	tv.park();
