@@ -71,7 +71,7 @@ const char* last_error_cstr();
 
 constexpr int kCounterSlots = 64;
 constexpr size_t kSmallSceneBytes = 128u << 10;  // C1 (486 spheres) is 47 KB, C3 2 KB, C4 (the one that wants the spill-free build) 490 KB
-constexpr unsigned kAdaptiveTailPixels = 2048;   // adaptive renders: below this many unfinished pixels, switch to one warp per pixel
+constexpr unsigned kAdaptiveTailPixels = 8192;   // adaptive renders: below this many unfinished pixels, switch to one warp per pixel (measured 256 / 2048 / 8192: profiles/r02_v2_adaptive_times.log)
 constexpr int kStatSlots = 16;                   // [0..3] = gs_stats totals; [4..] only written by the GS_DIVERGENCE_STATS diagnostic build
 constexpr size_t kWideMinPrims = 16384;          // scenes with at least this many primitives traverse the eight-wide tree (override: GS_BVH_WIDTH)
 
@@ -91,14 +91,14 @@ struct gs_scene {
 	std::unique_ptr<gs_bvh_node[]> h_nodes;  // copy of the caller's tree (filled by a helper thread while the layout runs)
 	size_t n_nodes = 0;
 	std::vector<int> h_node_to_dnode;   // ABI node -> DNode index (internal nodes), -1 for leaves
-	std::vector<int> h_leaf_code;       // ABI node -> leaf code (leaves)
+	std::unique_ptr<int[]> h_leaf_code;  // ABI node -> leaf code (leaves; entries of internal nodes are never read)
 	std::vector<int> h_bfs;             // internal ABI nodes in BFS order (= binary device order)
 	// eight-wide topology: slot k of wide node h holds ABI node w_kids[8h + k] (-1 = empty), w_child_base[h] = wide index of its
 	// first internal kid, w_prim_base[3h + kind] = first device primitive of that kind among its single-primitive leaf kids
 	std::vector<int> w_kids;
 	std::vector<int> w_child_base;
 	std::vector<uint32_t> w_prim_base;
-	std::vector<int> h_leaf_direct;     // ABI leaf -> device primitive index if the leaf is one freshly placed primitive the wide node can address by offset, else -1
+	std::unique_ptr<int[]> h_leaf_direct;  // ABI leaf -> device primitive index if the leaf is one freshly placed primitive the wide node can address by offset, else -1
 	int wide_depth = 0;
 	double origin_limit = 0.0;
 	double max_abs_coord = 0.0;

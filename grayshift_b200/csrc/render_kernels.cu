@@ -176,7 +176,10 @@ __global__ void __launch_bounds__(kBlock, (kF & 8) ? GS_MIN_BLOCKS + 1 : GS_MIN_
 						const uint32_t off = sample0 + rank, q = off / P.sample_count;
 						uint32_t pixel = pixel0 + q;
 						const uint32_t sample = off - q * P.sample_count + (kAdaptive ? s_rnd.round * P.sample_count : P.sample_begin);
-						if (kAdaptive) pixel = __ldcg(s_rnd.pixel_list + pixel);  // the lists are rewritten every round: read them past the (incoherent) L1
+						// the lists are rewritten every round by other SMs; the gpu-scope fences around the grid syncs invalidate this SM's
+						// L1 (CCTL.IVALL), so an ordinary cached load sees the new list -- a warp's lanes share a pixel, i.e. one line.
+						// (Reading it from L2 with ld.cg cost every regeneration an L2 round trip: -15 % on the final scene.)
+						if (kAdaptive) pixel = s_rnd.pixel_list[pixel];
 						path_begin(st, P.cam, P.seed, pixel, sample);
 						state = kSetup;
 					}

@@ -285,7 +285,8 @@ struct WideBuild {
 	std::vector<int> kids;        // 8 per wide node, ABI node index or -1
 	std::vector<int> child_base;  // wide index of the first internal kid
 	std::vector<int> of_bin;      // wide node -> the binary node it replaces
-	int depth = 0;
+	int depth = 0;                // levels of the eight-wide tree
+	int binary_depth = 0;         // deepest node of the binary tree (root = 0)
 };
 
 void build_wide_topology(const gs_bvh_node* N, size_t n_nodes, WideBuild& w) {
@@ -296,8 +297,10 @@ void build_wide_topology(const gs_bvh_node* N, size_t n_nodes, WideBuild& w) {
 	});
 	auto internal = [&](int a) { return N[a].ref_count == 0; };
 	// one wide node: collapse + octant slots; returns the number of internal kids
-	auto make_node = [&](int a, int* slot_kid) -> int {
+	// (depth_in = binary depth of node a; kid_depth[] = binary depths of the kids, in slot order)
+	auto make_node = [&](int a, int depth_in, int* slot_kid, int* slot_depth) -> int {
 		int kids[8] = {N[a].left, N[a].right, -1, -1, -1, -1, -1, -1};
+		int kd[8] = {depth_in + 1, depth_in + 1, 0, 0, 0, 0, 0, 0};
 		int n = 2;
 		while (n < 8) {
 			int best = -1;
@@ -306,7 +309,9 @@ void build_wide_topology(const gs_bvh_node* N, size_t n_nodes, WideBuild& w) {
 			if (best < 0) break;
 			const int c = kids[best];
 			kids[best] = N[c].left;
-			kids[n++] = N[c].right;
+			kids[n] = N[c].right;
+			kd[best] += 1; kd[n] = kd[best];
+			++n;
 		}
 		double centre[3];
 		for (int x = 0; x < 3; ++x) centre[x] = 0.5 * (N[a].bounds_min[x] + N[a].bounds_max[x]);
@@ -326,6 +331,7 @@ void build_wide_topology(const gs_bvh_node* N, size_t n_nodes, WideBuild& w) {
 					if (slot_kid[s] < 0 && (bk < 0 || score[k][s] > score[bk][bs])) { bk = k; bs = s; }
 			}
 			slot_kid[bs] = kids[bk];
+			slot_depth[bs] = kd[bk];
 			placed[bk] = true;
 		}
 		int n_int = 0;
@@ -334,7 +340,8 @@ void build_wide_topology(const gs_bvh_node* N, size_t n_nodes, WideBuild& w) {
 	};
 	// level by level: the nodes of a level are independent of each other (host threads), their internal kids -- in node
 	// order, then slot order -- are the next level: the same numbering a breadth-first queue gives
-	std::vector<int> level{0}, next, n_int;
+	std::vector<int> level{0}, next, n_int, level_depth{0}, next_depth, kid_depth;
+	std::atomic<int> deepest{0};
 	size_t base = 0;
 	while (!level.empty()) {
 		const size_t L = level.size();
@@ -342,20 +349,32 @@ void build_wide_topology(const gs_bvh_node* N, size_t n_nodes, WideBuild& w) {
 		w.child_base.resize(base + L);
 		w.of_bin.insert(w.of_bin.end(), level.begin(), level.end());
 		n_int.assign(L, 0);
-		parallel_for(L, [&](size_t i) { n_int[i] = make_node(level[i], w.kids.data() + (base + i) * 8); }, 2048);
+		kid_depth.assign(L * 8, 0);
+		parallel_for(L, [&](size_t i) {
+			n_int[i] = make_node(level[i], level_depth[i], w.kids.data() + (base + i) * 8, kid_depth.data() + i * 8);
+			int m = 0;
+			for (int s = 0; s < 8; ++s) m = std::max(m, kid_depth[i * 8 + s]);
+			int cur = deepest.load(std::memory_order_relaxed);
+			while (m > cur && !deepest.compare_exchange_weak(cur, m)) {}
+		}, 2048);
 		size_t total = 0;
 		for (size_t i = 0; i < L; ++i) { w.child_base[base + i] = n_int[i] ? (int)(base + L + total) : 0; total += (size_t)n_int[i]; }
 		next.assign(total, 0);
+		next_depth.assign(total, 0);
 		parallel_for(L, [&](size_t i) {
 			if (!n_int[i]) return;
-			int* out = next.data() + ((size_t)w.child_base[base + i] - (base + L));
+			const size_t at = (size_t)w.child_base[base + i] - (base + L);
+			int* out = next.data() + at;
+			int* outd = next_depth.data() + at;
 			const int* kid = w.kids.data() + (base + i) * 8;
-			for (int s = 0; s < 8; ++s) if (kid[s] >= 0 && internal(kid[s])) *out++ = kid[s];
+			for (int s = 0; s < 8; ++s) if (kid[s] >= 0 && internal(kid[s])) { *out++ = kid[s]; *outd++ = kid_depth[i * 8 + s]; }
 		}, 2048);
 		base += L;
 		level.swap(next);
+		level_depth.swap(next_depth);
 		++w.depth;
 	}
+	w.binary_depth = deepest.load();
 }
 }  // namespace
 
@@ -380,18 +399,19 @@ int layout_scene(gs_scene* s, const gs_scene_desc* d) {
 	}
 	struct Join { std::vector<std::thread>& t; ~Join() { for (auto& x : t) if (x.joinable()) x.join(); } } join_copiers{copiers};
 	lap("copy nodes (started)");
-	// tree check: children carry larger indices than their parent, so one ascending sweep sees every parent first
+	// tree check: children carry larger indices than their parent (validated), so "every node but the root has exactly one
+	// parent" already means one tree hanging off node 0.  (Its depth comes out of the topology pass below.)
 	{
-		std::vector<int8_t> depth(nN, -1);
-		depth[0] = 0;
-		for (size_t i = 0; i < nN; ++i) {
-			if (depth[i] < 0 || N[i].ref_count > 0) continue;
-			for (int c : {N[i].left, N[i].right}) {
-				if (depth[c] >= 0) return fail(GS_ERR_INVALID, "BVH is not a tree (node reached twice)");
-				if (depth[i] + 1 > kMaxStack - 4) return fail(GS_ERR_UNSUPPORTED, "BVH deeper than the traversal stack");
-				depth[c] = (int8_t)(depth[i] + 1);
-			}
-		}
+		std::unique_ptr<std::atomic<uint8_t>[]> parents(new std::atomic<uint8_t>[nN]);
+		parallel_for(nN, [&](size_t i) { parents[i].store(0, std::memory_order_relaxed); });
+		std::atomic<bool> twice{false};
+		parallel_for(nN, [&](size_t i) {
+			if (N[i].ref_count > 0) return;
+			if (parents[N[i].left].fetch_add(1, std::memory_order_relaxed) != 0 || parents[N[i].right].fetch_add(1, std::memory_order_relaxed) != 0) twice = true;
+		});
+		if (twice.load()) return fail(GS_ERR_INVALID, "BVH is not a tree (node reached twice)");
+		const long orphan = first_bad(nN, [&](size_t i) { return (i == 0) != (parents[i].load(std::memory_order_relaxed) == 0); });
+		if (orphan >= 0) return fail(GS_ERR_INVALID, orphan == 0 ? "BVH is not a tree (the root has a parent)" : "BVH node " + std::to_string(orphan) + " is not reachable from the root");
 	}
 	lap("tree check");
 
@@ -399,6 +419,7 @@ int layout_scene(gs_scene* s, const gs_scene_desc* d) {
 	WideBuild wb;
 	const bool root_leaf = N[0].ref_count > 0;
 	if (!root_leaf) build_wide_topology(N, nN, wb);
+	if (wb.binary_depth > kMaxStack - 4) return fail(GS_ERR_UNSUPPORTED, "BVH deeper than the traversal stack");
 	const size_t nW = wb.of_bin.size();
 	lap("wide topology");
 
@@ -409,8 +430,8 @@ int layout_scene(gs_scene* s, const gs_scene_desc* d) {
 	sph_src.reserve(d->n_spheres); quad_src.reserve(d->n_quads); tri_src.reserve(d->n_triangles);
 	std::vector<uint32_t> refs;
 	refs.reserve(d->n_prim_refs);
-	s->h_leaf_code.assign(nN, 0);
-	s->h_leaf_direct.assign(nN, -1);
+	s->h_leaf_code.reset(new int[nN]);     // uninitialised: every leaf's entry is written below, nothing else is read
+	s->h_leaf_direct.reset(new int[nN]);
 	s->w_prim_base.assign(nW * 3, 0u);
 	bool any_moving = false, any_rot = false;
 	auto emit_leaf = [&](int leaf) {
@@ -433,6 +454,7 @@ int layout_scene(gs_scene* s, const gs_scene_desc* d) {
 			}
 		}
 		s->h_leaf_code[leaf] = leaf_code(first, (uint32_t)nd.ref_count);
+		s->h_leaf_direct[leaf] = -1;
 		if (nd.ref_count == 1) {
 			// single-primitive leaf: (kind << 25 | index) in the link itself, count field 0 -- no dependent load from `refs`
 			const uint32_t r = refs.back(), kind = r >> kRefKindShift, idx = r & kRefIndexMask;
@@ -530,6 +552,7 @@ int layout_scene(gs_scene* s, const gs_scene_desc* d) {
 						refs[next_ref++] = last_ref;
 					}
 					s->h_leaf_code[c] = leaf_code(first, (uint32_t)N[c].ref_count);
+					s->h_leaf_direct[c] = -1;
 					if (N[c].ref_count == 1) {
 						const uint32_t kind = last_ref >> kRefKindShift, idx = last_ref & kRefIndexMask;
 						s->h_leaf_code[c] = leaf_code((kind << 25) | idx, 0u);

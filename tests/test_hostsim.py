@@ -137,3 +137,124 @@ def test_random_scene_graphs_on_the_host(seed, tmp_path):
             assert np.array_equal(ids, oid), f"max_leaf {max_leaf} width {width}: {int((ids != oid).sum())} id mismatches"
             hit = oid >= 0
             assert np.all(np.abs(t[hit] - ot[hit]) <= 1e-9 * np.abs(ot[hit]))
+
+
+# ---- hand-made descriptions: validation (ADVICE: nothing aborts across the boundary) and the layout's rarely taken paths ----------
+def _desc_of_spheres(centres, nodes, refs, radius=0.5):
+    """a flat description over `centres` with an explicit tree: nodes = [(left, right, first_ref, ref_count), ...]"""
+    n = len(centres)
+    sph = (ffi.gs_sphere * n)()
+    for i, c in enumerate(centres):
+        sph[i].center[:] = c
+        sph[i].radius = radius
+        sph[i].material = 0
+        sph[i].prim_id = 100 + i
+        sph[i].order = i
+        sph[i].uv_rotation[:] = (1.0, 0.0)
+    mats = (ffi.gs_material * 1)()
+    mats[0].kind, mats[0].texture = 0, 0
+    texs = (ffi.gs_texture * 1)()
+    texs[0].kind, texs[0].a, texs[0].b = 0, -1, -1
+    texs[0].color[:] = (0.5, 0.5, 0.5)
+    nd = (ffi.gs_bvh_node * len(nodes))()
+    pr = (C.c_uint32 * len(refs))(*refs)
+
+    def bounds(i):
+        l, r, first, count = nodes[i]
+        idx = [refs[first + k] & 0x3fffffff for k in range(count)] if count > 0 else None
+        if idx is None:
+            (a0, a1), (b0, b1) = bounds(l), bounds(r)
+            return np.minimum(a0, b0), np.maximum(a1, b1)
+        pts = np.array([centres[k] for k in idx], dtype=float)
+        return pts.min(0) - radius, pts.max(0) + radius
+    for i, (l, r, first, count) in enumerate(nodes):
+        lo, hi = bounds(i)
+        nd[i].bounds_min[:] = lo
+        nd[i].bounds_max[:] = hi
+        nd[i].left, nd[i].right, nd[i].first_ref, nd[i].ref_count = l, r, first, count
+    d = ffi.gs_scene_desc()
+    d.abi_version = ffi.GS_ABI_VERSION
+    d.spheres, d.n_spheres = C.cast(sph, C.POINTER(ffi.gs_sphere)), n
+    d.nodes, d.n_nodes = C.cast(nd, C.POINTER(ffi.gs_bvh_node)), len(nodes)
+    d.prim_refs, d.n_prim_refs = C.cast(pr, C.POINTER(C.c_uint32)), len(refs)
+    d.materials, d.n_materials = C.cast(mats, C.POINTER(ffi.gs_material)), 1
+    d.textures, d.n_textures = C.cast(texs, C.POINTER(ffi.gs_texture)), 1
+    return d, (sph, mats, texs, nd, pr)
+
+
+def _create(d, width):
+    L = hostsim()
+    h = C.c_void_p()
+    rc = L.hs_scene_create(C.byref(d), width, C.byref(h))
+    return rc, L.hs_last_error().decode(), h
+
+
+def test_layout_rejects_what_is_not_a_tree():
+    centres = [(0, 0, 0), (2, 0, 0), (4, 0, 0)]
+    # node 2 has two parents
+    d, keep = _desc_of_spheres(centres, [(1, 2, 0, 0), (2, 3, 0, 0), (0, 0, 0, 1), (0, 0, 1, 1)], [0, 1])
+    rc, msg, _ = _create(d, 2)
+    assert rc == ffi.GS_ERR_INVALID and "tree" in msg
+    # node 3 hangs in the air (the root's children are 1 and 2)
+    d, keep = _desc_of_spheres(centres, [(1, 2, 0, 0), (0, 0, 0, 1), (0, 0, 1, 1), (0, 0, 2, 1)], [0, 1, 2])
+    rc, msg, _ = _create(d, 2)
+    assert rc == ffi.GS_ERR_INVALID and "not reachable" in msg
+    # negative ref_count: neither an internal node nor a leaf (ADVICE)
+    d, keep = _desc_of_spheres(centres, [(1, 2, 0, 0), (0, 0, 0, 1), (0, 0, 1, 1)], [0, 1])
+    keep[3][2].ref_count = -1
+    rc, msg, _ = _create(d, 2)
+    assert rc == ffi.GS_ERR_INVALID and "negative ref_count" in msg
+    # a non-zero count with a null array
+    d, keep = _desc_of_spheres(centres, [(1, 2, 0, 0), (0, 0, 0, 1), (0, 0, 1, 1)], [0, 1])
+    d.n_media = 1
+    rc, msg, _ = _create(d, 2)
+    assert rc == ffi.GS_ERR_INVALID and "null media" in msg
+    # a chain deeper than the traversal stacks
+    n = 80
+    centres = [(2.0 * i, 0, 0) for i in range(n)]
+    nodes, refs = [], list(range(n))
+    for i in range(n - 1):       # internal node 2i: left = leaf 2i+1 (sphere i), right = next internal (or the last leaf)
+        nodes.append((2 * i + 1, 2 * i + 2, 0, 0))
+        nodes.append((0, 0, i, 1))
+    nodes.append((0, 0, n - 1, 1))
+    d, keep = _desc_of_spheres(centres, nodes, refs)
+    rc, msg, _ = _create(d, 2)
+    assert rc == ffi.GS_ERR_UNSUPPORTED and "deeper" in msg
+
+
+@pytest.mark.parametrize("width", [2, 8])
+def test_a_primitive_referenced_by_two_leaves(width):
+    """spatial-split style trees reference a primitive from several leaves: the layout falls back to its serial walk (first
+    reference places the primitive, later ones go through the leaf-link side table of the wide tree)"""
+    rng = np.random.default_rng(4)
+    centres = [tuple(rng.uniform(-4, 4, 3)) for _ in range(6)]
+    # root -> (A, B); A = leaf [0, 1, 2]; B -> (leaf [2, 3], C); C -> (leaf [4], leaf [5, 0])
+    refs = [0, 1, 2, 2, 3, 4, 5, 0]
+    nodes = [(1, 2, 0, 0), (0, 0, 0, 3), (3, 4, 0, 0), (0, 0, 3, 2), (5, 6, 0, 0), (0, 0, 5, 1), (0, 0, 6, 2)]
+    d, keep = _desc_of_spheres(centres, nodes, refs)
+    rc, msg, h = _create(d, width)
+    assert rc == 0, msg
+    L = hostsim()
+    n = 4000
+    o = rng.uniform(-8, 8, (n, 3))
+    tgt = np.array(centres)[rng.integers(0, 6, n)] + rng.normal(size=(n, 3)) * 0.4
+    rays = np.concatenate([o, tgt - o, np.zeros((n, 1))], axis=1)
+    ids, t = np.empty(n, np.int32), np.empty(n, np.float64)
+    assert L.hs_trace_closest(h, rays.ctypes.data, n, 0.001, 1e300, ids.ctypes.data, t.ctypes.data, None) == 0
+    # brute force
+    best_t, best = np.full(n, np.inf), np.full(n, -1)
+    dd = rays[:, 3:6]
+    a = (dd * dd).sum(1)
+    for k, c in enumerate(centres):
+        oc = np.array(c) - o
+        hh = (dd * oc).sum(1)
+        disc = hh * hh - a * ((oc * oc).sum(1) - 0.25)
+        ok = disc >= 0
+        sq = np.sqrt(np.where(ok, disc, 0))
+        for root in ((hh - sq) / a, (hh + sq) / a):
+            take = ok & (root > 0.001) & (root < best_t) & ~((best == k))
+            best_t = np.where(take, root, best_t)
+            best = np.where(take, k, best)
+            ok = ok & ~take & (best != k)
+    assert np.array_equal(ids, np.where(best >= 0, 100 + best, -1))
+    L.hs_scene_destroy(h)
