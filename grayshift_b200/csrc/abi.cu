@@ -231,6 +231,7 @@ int gs_issue_fixed(gs_scene* s, const DCamera& cam, uint64_t seed, uint32_t samp
 	p.work_counter = next_counter(s);
 	p.stats = s->stats;
 	p.pixel_list = nullptr; p.n_list = nullptr; p.lum = nullptr;  // every pixel, no luminance statistics
+	p.rounds_in_kernel = false; p.round0 = 0; p.work_counter2 = nullptr; p.n_pixels = 0; p.tail_pixels = 0; p.max_samples = 0; p.confidence_sq = p.tolerance_sq = 0.0;
 	p.small_scene = s->small_scene;
 	p.wide = s->wide;
 	GS_CUDA(cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned long long), st));
@@ -310,6 +311,33 @@ int gs_render_adaptive_accumulate(gs_scene* s, const gs_camera* camera, const gs
 	p.tail_pixels = tail_pixels;
 	GS_CUDA(cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned long long), st));
 	GS_CUDA(cudaMemsetAsync(p.work_counter2, 0, sizeof(unsigned long long), st));
+	static const bool host_rounds = [] { const char* e = std::getenv("GS_ADAPTIVE_ROUNDS"); return e && std::strcmp(e, "host") == 0; }();
+	p.rounds_in_kernel = !host_rounds;
+	p.round0 = 0;
+	if (host_rounds) {
+		// The round-1 scheme, kept for A/B: one launch per batch + the stop test, a 4-byte "anyone left?" read after batches
+		// 1, 2, 4, 8 ... (synchronises the stream), the tail kernel once few pixels are left.
+		unsigned which = 0;
+		for (unsigned long long r = 0; r < rounds; ++r) {
+			const unsigned cur = (unsigned)(r & 1ull), nxt = cur ^ 1u;
+			p.round0 = (unsigned)r;
+			p.work_counter = next_counter(s);
+			GS_CUDA(cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned long long), st));
+			GS_CUDA(cudaMemsetAsync(s->px_count.p + nxt, 0, sizeof(unsigned), st));
+			GS_CUDA(launch_render_fixed(p, s->sm_count, false, s->has_triangles, st));
+			GS_CUDA(launch_adaptive_decide(p, cur, st));
+			s->launches += 2;
+			which = nxt;
+			if (((r + 1ull) & r) == 0ull && r + 1 < rounds) {
+				unsigned left = 0;
+				GS_CUDA(cudaMemcpyAsync(&left, s->px_count.p + nxt, sizeof left, cudaMemcpyDeviceToHost, st));
+				GS_CUDA(cudaStreamSynchronize(st));
+				if (left <= tail_pixels) break;
+			}
+		}
+		GS_CUDA(cudaMemcpyAsync(s->px_count.p + 2, &which, sizeof which, cudaMemcpyHostToDevice, st));
+		GS_CUDA(cudaStreamSynchronize(st));  // `which` is a stack variable
+	} else
 	// every batch round in one cooperative launch (render, grid sync, stop test, grid sync ...) until at most
 	// kAdaptiveTailPixels pixels are left; then one warp per remaining pixel finishes its loop.  No host round trip.
 	GS_CUDA(launch_render_fixed(p, s->sm_count, false, s->has_triangles, st));

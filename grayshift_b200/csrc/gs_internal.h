@@ -23,6 +23,8 @@ struct RenderParams {
 	double2* lum;                          // per pixel (sum of luminance, sum of its square), camera.rs:132-133,146-147
 	double confidence_sq, tolerance_sq;    // the stop test of camera.rs:150-164
 	unsigned max_samples, n_pixels, tail_pixels;  // n_pixels = capacity of each list; the rounds end once <= tail_pixels pixels are left
+	bool rounds_in_kernel;                 // false: this launch renders ONE batch (round0) and the host launches the stop test (A/B alternative)
+	unsigned round0;
 	bool small_scene;                      // nodes + primitives <= kSmallSceneBytes: the launch takes the 6-CTAs-per-SM build
 	bool wide;                             // traverse sc.nodes8 (eight-wide tree) instead of sc.nodes
 };
@@ -46,6 +48,7 @@ struct AdaptiveTailParams {  // the last few pixels: one warp per pixel runs the
 cudaError_t launch_render_fixed(const RenderParams& p, int sm_count, bool count_nodes, bool triangles, cudaStream_t stream);
 cudaError_t launch_adaptive_init(uint32_t* list, unsigned* n_list, unsigned pixel_begin, unsigned pixel_stride, unsigned n_pixels, cudaStream_t stream);
 cudaError_t launch_adaptive_tail(const AdaptiveTailParams& p, unsigned n_upper, int sm_count, bool wide, cudaStream_t stream);
+cudaError_t launch_adaptive_decide(const RenderParams& p, unsigned cur, cudaStream_t stream);  // host-driven rounds only
 cudaError_t launch_resolve(const float4* accum, int n_pixels, float* out_rgb, unsigned* out_counts, cudaStream_t stream);
 cudaError_t launch_resolve_rgb8(const float4* accum, int n_pixels, unsigned char* out_rgb8, unsigned* out_counts, cudaStream_t stream);
 cudaError_t launch_camera_rays(const DCamera& cam, unsigned long long seed, unsigned sample, int pixel_begin, int pixel_end, double* rays_out,

@@ -74,8 +74,9 @@ __global__ void __launch_bounds__(kBlock, (kF & 8) ? GS_MIN_BLOCKS + 1 : GS_MIN_
 	// shared memory -- as registers these seven values spilled the traversal loop (-27 % on the final scene)
 	__shared__ struct { unsigned long long total_items; const uint32_t* pixel_list; unsigned long long* work_counter; unsigned round; } s_rnd;
 	if (kAdaptive && threadIdx.x == 0) {
-		s_rnd.total_items = (unsigned long long)__ldcg(P.n_list) * P.sample_count;
-		s_rnd.pixel_list = P.pixel_list; s_rnd.work_counter = P.work_counter; s_rnd.round = 0u;
+		// (host-driven rounds: this launch is round P.round0 on list P.round0 & 1; in-kernel rounds start at 0)
+		s_rnd.total_items = (unsigned long long)__ldcg(P.n_list + (P.round0 & 1u)) * P.sample_count;
+		s_rnd.pixel_list = P.pixel_list + (size_t)(P.round0 & 1u) * P.n_pixels; s_rnd.work_counter = P.work_counter; s_rnd.round = P.round0;
 	}
 	__shared__ uint8_t s_perm[256];
 	__shared__ float4 s_top[kTopNodes > 0 ? kTopNodes * 4 : 1];
@@ -287,6 +288,10 @@ __global__ void __launch_bounds__(kBlock, (kF & 8) ? GS_MIN_BLOCKS + 1 : GS_MIN_
 		if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(P.stats + 1, P.total_items);  // every work item starts exactly one path
 		break;
 	}
+	if (!P.rounds_in_kernel) {  // host-driven rounds: the stop test is the next launch
+		if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(P.stats + 1, s_rnd.total_items);
+		break;
+	}
 	// ---- between two batches: Camera::sample's stop test (camera.rs:150-164) for every pixel of this round's list ----
 	// (the whole grid is co-resident: cooperative launch, persistent CTAs)
 	const unsigned cur = s_rnd.round & 1u, nxt = cur ^ 1u;
@@ -361,6 +366,38 @@ __global__ void adaptive_init_kernel(uint32_t* __restrict__ list, unsigned* __re
 	const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
 	if (k < n_pixels) list[k] = pixel_begin + k * pixel_stride;
 	if (k == 0) { n_list[0] = n_pixels; n_list[1] = 0u; n_list[2] = 0u; }
+}
+
+// The stop test as a kernel of its own: the host-driven alternative to the in-kernel rounds (one render launch + this per batch;
+// GS_ADAPTIVE_ROUNDS=host), kept for A/B measurements.
+__global__ void adaptive_decide_kernel(const uint32_t* __restrict__ list, const unsigned* __restrict__ n_in, uint32_t* __restrict__ next,
+                                       unsigned* __restrict__ n_out, const float4* __restrict__ accum, const double2* __restrict__ lum,
+                                       double confidence_sq, double tolerance_sq, unsigned max_samples) {
+	const unsigned n = *n_in;
+	const unsigned lane = threadIdx.x & 31u;
+	for (unsigned base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += gridDim.x * blockDim.x) {
+		const unsigned k = base + lane;
+		bool more = false;
+		uint32_t pixel = 0;
+		if (k < n) {
+			pixel = list[k];
+			const double sample_count = (double)accum[pixel].w;  // exact: one 1.0f per path, far below 2^24
+			const double2 s = lum[pixel];
+			const double mean = s.x / sample_count;  // camera.rs:150-158
+			const double variance_sq = 1.0 / (sample_count - 1.0) * (s.y - s.x * s.x / sample_count);
+			const double convergence_sq = confidence_sq * variance_sq / sample_count;
+			const bool converged = convergence_sq < mean * mean * tolerance_sq;
+			const unsigned sc_u32 = sample_count >= 4294967295.0 ? 4294967295u : (unsigned)sample_count;
+			more = !converged && !(sc_u32 > max_samples);  // camera.rs:162-164
+		}
+		const unsigned m = __ballot_sync(kFull, more);  // one atomic per warp; the order of the list does not matter
+		if (m) {
+			unsigned slot = 0;
+			if (lane == 0) slot = atomicAdd(n_out, (unsigned)__popc(m));
+			slot = __shfl_sync(kFull, slot, 0);
+			if (more) next[slot + __popc(m & ((1u << lane) - 1u))] = pixel;
+		}
+	}
 }
 
 // The tail of an adaptive render: when only a few pixels are still sampling, a launch per batch costs more than it
@@ -553,7 +590,7 @@ cudaError_t launch_render_fixed(const RenderParams& p, int sm_count, bool count_
 	void* args[] = {const_cast<RenderParams*>(&p)};
 	switch (variant) {
 #define X(v) case v: \
-		if ((v) & 4) return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(&render_fixed_kernel<v>), dim3((unsigned)grid), dim3(kBlock), args, 0, stream); \
+		if (((v) & 4) && p.rounds_in_kernel) return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(&render_fixed_kernel<v>), dim3((unsigned)grid), dim3(kBlock), args, 0, stream); \
 		render_fixed_kernel<v><<<(unsigned)grid, kBlock, 0, stream>>>(p); break;
 		GS_FIXED_VARIANTS(X)
 #undef X
@@ -577,6 +614,14 @@ cudaError_t launch_adaptive_tail(const AdaptiveTailParams& p, unsigned n_upper, 
 	if (blocks_needed < grid) grid = blocks_needed ? blocks_needed : 1;
 	if (wide) adaptive_tail_kernel<18><<<(unsigned)grid, kBlock, 0, stream>>>(p);
 	else adaptive_tail_kernel<2><<<(unsigned)grid, kBlock, 0, stream>>>(p);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_adaptive_decide(const RenderParams& p, unsigned cur, cudaStream_t stream) {
+	const unsigned blocks = (p.n_pixels + 255) / 256;
+	adaptive_decide_kernel<<<blocks < 1184u ? (blocks ? blocks : 1u) : 1184u, 256, 0, stream>>>(
+		p.pixel_list + (size_t)cur * p.n_pixels, p.n_list + cur, p.pixel_list + (size_t)(cur ^ 1u) * p.n_pixels, p.n_list + (cur ^ 1u), p.accum, p.lum,
+		p.confidence_sq, p.tolerance_sq, p.max_samples);
 	return cudaGetLastError();
 }
 
