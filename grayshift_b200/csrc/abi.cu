@@ -311,12 +311,17 @@ int gs_render_adaptive_accumulate(gs_scene* s, const gs_camera* camera, const gs
 	p.tail_pixels = tail_pixels;
 	GS_CUDA(cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned long long), st));
 	GS_CUDA(cudaMemsetAsync(p.work_counter2, 0, sizeof(unsigned long long), st));
-	static const bool host_rounds = [] { const char* e = std::getenv("GS_ADAPTIVE_ROUNDS"); return e && std::strcmp(e, "host") == 0; }();
+	// Who drives the batch rounds.  Default: the host (one render launch + the stop test per batch, a 4-byte "anyone left?" read after
+	// batches 1, 2, 4, 8 ...).  GS_ADAPTIVE_ROUNDS=kernel: all rounds inside one cooperative launch with grid-wide syncs in between --
+	// no host round trip, but measured 2...15 % slower on every scene of main.rs (profiles/r02_v4_adaptive_rounds_host_vs_kernel.log:
+	// the final scene at 400x400 141 vs 165 ms): CTAs that finish a round early spin at the grid barrier next to the ones still
+	// rendering and every arrival invalidates the SM's L1, where a kernel boundary simply frees the SM.
+	static const bool host_rounds = [] { const char* e = std::getenv("GS_ADAPTIVE_ROUNDS"); return !(e && std::strcmp(e, "kernel") == 0); }();
 	p.rounds_in_kernel = !host_rounds;
 	p.round0 = 0;
 	if (host_rounds) {
-		// The round-1 scheme, kept for A/B: one launch per batch + the stop test, a 4-byte "anyone left?" read after batches
-		// 1, 2, 4, 8 ... (synchronises the stream), the tail kernel once few pixels are left.
+		// one launch per batch + the stop test; after batches 1, 2, 4, 8 ... a 4-byte read tells whether to go on, to hand the
+		// last few pixels to the tail kernel, or to stop (synchronises the stream)
 		unsigned which = 0;
 		for (unsigned long long r = 0; r < rounds; ++r) {
 			const unsigned cur = (unsigned)(r & 1ull), nxt = cur ^ 1u;
@@ -338,8 +343,8 @@ int gs_render_adaptive_accumulate(gs_scene* s, const gs_camera* camera, const gs
 		GS_CUDA(cudaMemcpyAsync(s->px_count.p + 2, &which, sizeof which, cudaMemcpyHostToDevice, st));
 		GS_CUDA(cudaStreamSynchronize(st));  // `which` is a stack variable
 	} else
-	// every batch round in one cooperative launch (render, grid sync, stop test, grid sync ...) until at most
-	// kAdaptiveTailPixels pixels are left; then one warp per remaining pixel finishes its loop.  No host round trip.
+	// (alternative) every batch round in one cooperative launch (render, grid sync, stop test, grid sync ...) until at most
+	// tail_pixels pixels are left; then one warp per remaining pixel finishes its loop.  No host round trip.
 	GS_CUDA(launch_render_fixed(p, s->sm_count, false, s->has_triangles, st));
 	AdaptiveTailParams tp;
 	tp.sc = s->ds; tp.cam = p.cam; tp.seed = seed;

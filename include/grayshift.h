@@ -265,9 +265,10 @@ int gs_render_accumulate(gs_scene* scene, const gs_camera* camera, uint64_t seed
 /* The adaptive sampler of Camera::sample (camera.rs:125-171) with the reference's batch / stop-test
  * semantics, for pixels pixel_begin, pixel_begin + pixel_stride, ... (ranks interleave pixels; every
  * pixel's whole batch loop runs on one GPU).  Leaves (sum r, sum g, sum b, count) in d_accum[pixel]; the entries
- * of these pixels must be ZERO on entry (the count doubles as the sampler's running sample_count).  Asynchronous like
- * gs_render_accumulate: every batch round runs inside one cooperative launch (render, grid-wide sync, stop test), a second
- * launch finishes the last few pixels with one warp each -- no host round trip between batches. */
+ * of these pixels must be ZERO on entry (the count doubles as the sampler's running sample_count).  Runs one launch per
+ * batch over the pixels still sampling plus the stop test, and reads back a 4-byte "any left?" after batches 1, 2, 4, ...:
+ * it synchronises `cuda_stream` a few times and has finished issuing work when it returns.  (GS_ADAPTIVE_ROUNDS=kernel in the
+ * environment selects the fully asynchronous variant -- every round inside one cooperative launch -- which measured slower.) */
 int gs_render_adaptive_accumulate(gs_scene* scene, const gs_camera* camera, const gs_sample_settings* settings,
                                   uint64_t seed, uint32_t pixel_begin, uint32_t pixel_stride, void* d_accum,
                                   void* cuda_stream);
