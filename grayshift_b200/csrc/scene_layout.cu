@@ -425,11 +425,9 @@ int layout_scene(gs_scene* s, const gs_scene_desc* d) {
 
 	// ---- device order of the primitives: depth-first over the wide tree; at a node first the primitives of its
 	// single-primitive leaf children (addressable as base + offset from the node), then those of its larger leaves ----
-	std::vector<int> sph_new(d->n_spheres, -1), quad_new(d->n_quads, -1), tri_new(d->n_triangles, -1);
+	std::vector<int> sph_new, quad_new, tri_new;  // "placed already?" tables of the serial walk only
 	std::vector<int> sph_src, quad_src, tri_src;
-	sph_src.reserve(d->n_spheres); quad_src.reserve(d->n_quads); tri_src.reserve(d->n_triangles);
 	std::vector<uint32_t> refs;
-	refs.reserve(d->n_prim_refs);
 	s->h_leaf_code.reset(new int[nN]);     // uninitialised: every leaf's entry is written below, nothing else is read
 	s->h_leaf_direct.reset(new int[nN]);
 	s->w_prim_base.assign(nW * 3, 0u);
@@ -475,6 +473,12 @@ int layout_scene(gs_scene* s, const gs_scene_desc* d) {
 		});
 		unique_refs = !dup.load();
 	}
+	lap("  order: unique-reference check");
+	if (root_leaf || !unique_refs) {
+		sph_new.assign(d->n_spheres, -1); quad_new.assign(d->n_quads, -1); tri_new.assign(d->n_triangles, -1);
+		sph_src.reserve(d->n_spheres); quad_src.reserve(d->n_quads); tri_src.reserve(d->n_triangles);
+		refs.reserve(d->n_prim_refs);
+	}
 	if (root_leaf) emit_leaf(0);
 	else if (unique_refs) {
 		// per wide node: primitives (per kind) and references of its own leaf kids, singles and larger leaves apart
@@ -494,6 +498,7 @@ int layout_scene(gs_scene* s, const gs_scene_desc* d) {
 			}
 			own[h] = o;
 		}, 4096);
+		lap("  order: own counts");
 		// subtree totals bottom-up (kids carry larger indices), then start offsets top-down in the walk's order:
 		// own singles, own larger leaves, then the internal kids' subtrees in slot order
 		struct Tot { uint32_t prim[3], refs; };
@@ -525,6 +530,7 @@ int layout_scene(gs_scene* s, const gs_scene_desc* d) {
 				cur.refs += sub[c].refs;
 			}
 		}
+		lap("  order: subtree offsets");
 		sph_src.assign(d->n_spheres, 0); quad_src.assign(d->n_quads, 0); tri_src.assign(d->n_triangles, 0);
 		refs.assign(d->n_prim_refs, 0u);
 		std::atomic<bool> moving_seen{false};
