@@ -456,8 +456,13 @@ __device__ __forceinline__ void leaf_intersect(const DeviceScene& sc, const Ray&
 // ==========================================================================================
 // Traversal policy 1: the binary tree (DNode).  State = (node, sp) + the per-thread stack of links.
 // ==========================================================================================
+#ifndef GS_POP_CULL
+#define GS_POP_CULL 0  // binary tree: push the far child's entry distance with its link and drop it at pop time if the closest hit
+                       // has come nearer since (host simulation: 32...48 % of the pops are stale on C1 / C4 / C5, each one a wasted node
+                       // or leaf visit) -- costs a second stack word per push
+#endif
 struct Trav2 {
-	static constexpr int kStackWords = kMaxStack;
+	static constexpr int kStackWords = GS_POP_CULL ? 2 * kMaxStack : kMaxStack;
 	int node;   // current node index / leaf code, kStackSentinel when the ray is finished
 	int sp;     // stack entries in use
 	Hit best;
@@ -465,13 +470,27 @@ struct Trav2 {
 	template <class Stack>
 	__device__ __forceinline__ void init(const DeviceScene& sc, const Ray&, const Stack& stack, double tmax) {
 		stack.set(0, kStackSentinel);
+#if GS_POP_CULL
+		stack.set(1, 0);  // entry distance 0: the sentinel is never culled
+		sp = 2;
+#else
 		sp = 1;
+#endif
 		node = sc.root;
 		best.t = tmax; best.ref = kNoHit; best.u = 0.f; best.v = 0.f;
 	}
 	__device__ __forceinline__ void park() { node = kStackSentinel; sp = 0; }
 	__device__ __forceinline__ bool done() const { return node == kStackSentinel; }
 	__device__ __forceinline__ bool wants_node() const { return node >= 0; }
+	template <class Stack>
+	__device__ __forceinline__ void pop(const Stack& stack, const RayConsts& rc) {
+#if GS_POP_CULL
+		float en;
+		do { sp -= 2; node = stack.get(sp); en = __int_as_float(stack.get(sp + 1)); } while (en > rc.tmax32);
+#else
+		node = stack.get(--sp);
+#endif
+	}
 	__device__ __forceinline__ bool wants_leaf() const { return node < 0 && node != kStackSentinel; }
 	__device__ __forceinline__ uint32_t pending_leaf_kind() const { return ((uint32_t)(-1 - node) >> 4) >> 25; }  // diagnostics only
 
@@ -537,16 +556,26 @@ struct Trav2 {
 		// dependent L1 round trips.)
 		const bool first0 = h0 && (!h1 || !(en1 < en0));
 		const int first = first0 ? link0 : link1, second = first0 ? link1 : link0;
-		if (h0 && h1) stack.set(sp++, second);
-		if (h0 || h1) node = first;
-		else node = stack.get(--sp);
+#if GS_POP_CULL
+		if (h0 && h1) { stack.set(sp, second); stack.set(sp + 1, __float_as_int(first0 ? en1 : en0)); sp += 2; }
 #else
-		if (!h0 && !h1) { node = stack.get(--sp); }
+		if (h0 && h1) stack.set(sp++, second);
+#endif
+		if (h0 || h1) node = first;
+		else pop(stack, rc);
+#else
+		if (!h0 && !h1) { pop(stack, rc); }
 		else {
 			int near = link0, far = link1;
 			if (h0 && h1) {
-				if (en1 < en0) { int tmp = near; near = far; far = tmp; }
+				float far_en = en1;
+				if (en1 < en0) { int tmp = near; near = far; far = tmp; far_en = en0; }
+#if GS_POP_CULL
+				stack.set(sp, far); stack.set(sp + 1, __float_as_int(far_en)); sp += 2;
+#else
+				(void)far_en;
 				stack.set(sp++, far);
+#endif
 				node = near;
 			} else node = h0 ? near : far;
 		}
@@ -557,7 +586,7 @@ struct Trav2 {
 	template <bool kTris, class Stack>
 	__device__ __forceinline__ void leaf_step(const DeviceScene& sc, const Ray& r, RayConsts& rc, double tmin, const Stack& stack) {
 		leaf_intersect<kTris>(sc, r, rc, tmin, best, node);
-		node = stack.get(--sp);
+		pop(stack, rc);
 	}
 };
 

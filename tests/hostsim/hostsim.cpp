@@ -48,3 +48,48 @@ int hs_trace_closest(gs_scene* s, const double* rays, size_t n, double tmin, dou
 	return 0;
 }
 }
+
+// ---- experiment: how many popped nodes are already behind the closest hit?  (binary tree; decides whether storing the entry
+// distance with a pushed link, to cull at pop time, is worth its stack traffic) ----
+extern "C" int hs_pop_stats(gs_scene* s, const double* rays, size_t n, double tmin, double tmax, uint64_t* out) {
+	using namespace gs;
+	uint64_t visits = 0, pops = 0, stale = 0, leaf_tests = 0, stale_leaf = 0;
+	if (!s->nodes) return 1;
+	for (size_t k = 0; k < n; ++k) {
+		const double* rp = rays + k * 7;
+		Ray r;
+		r.ox = rp[0]; r.oy = rp[1]; r.oz = rp[2]; r.dx = rp[3]; r.dy = rp[4]; r.dz = rp[5]; r.time = rp[6];
+		RayConsts rc = ray_consts(r, tmax);
+		int stack[kMaxStack]; float sten[kMaxStack];
+		int sp = 0;
+		int node = s->ds.root;
+		Hit best; best.t = tmax; best.ref = kNoHit; best.u = best.v = 0.f;
+		float cur_en = 0.f;
+		for (;;) {
+			if (node >= 0) {
+				++visits;
+				const DNode& nd = s->nodes[node];
+				auto slab = [&](float c, float h, float id, float oi, float& tn, float& tf) { const float tm = fmaf(c, id, -oi), th = h * fabsf(id); tn = tm - th; tf = tm + th; };
+				float n0x, f0x, n0y, f0y, n0z, f0z, n1x, f1x, n1y, f1y, n1z, f1z;
+				slab(nd.xy0.x, nd.xy0.y, rc.idx, rc.oix, n0x, f0x); slab(nd.xy0.z, nd.xy0.w, rc.idy, rc.oiy, n0y, f0y); slab(nd.z01.x, nd.z01.y, rc.idz, rc.oiz, n0z, f0z);
+				slab(nd.xy1.x, nd.xy1.y, rc.idx, rc.oix, n1x, f1x); slab(nd.xy1.z, nd.xy1.w, rc.idy, rc.oiy, n1y, f1y); slab(nd.z01.z, nd.z01.w, rc.idz, rc.oiz, n1z, f1z);
+				const float en0 = fmaxf(fmaxf(n0x, n0y), fmaxf(n0z, 0.f)), ex0 = fminf(fminf(f0x, f0y), fminf(f0z, rc.tmax32));
+				const float en1 = fmaxf(fmaxf(n1x, n1y), fmaxf(n1z, 0.f)), ex1 = fminf(fminf(f1x, f1y), fminf(f1z, rc.tmax32));
+				const bool h0 = en0 <= ex0, h1 = en1 <= ex1;
+				const bool first0 = h0 && (!h1 || !(en1 < en0));
+				const int first = first0 ? nd.link.x : nd.link.y, second = first0 ? nd.link.y : nd.link.x;
+				if (h0 && h1) { stack[sp] = second; sten[sp] = first0 ? en1 : en0; ++sp; }
+				if (h0 || h1) { node = first; cur_en = first0 ? en0 : en1; continue; }
+			} else {
+				++leaf_tests;
+				if (cur_en > rc.tmax32) ++stale_leaf;
+				leaf_intersect<false>(s->ds, r, rc, tmin, best, node);
+			}
+			if (sp == 0) break;
+			--sp; node = stack[sp]; cur_en = sten[sp]; ++pops;
+			if (cur_en > rc.tmax32) ++stale;
+		}
+	}
+	out[0] = visits; out[1] = pops; out[2] = stale; out[3] = leaf_tests; out[4] = stale_leaf;
+	return 0;
+}
