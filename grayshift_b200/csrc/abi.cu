@@ -161,6 +161,7 @@ int gs_scene_set_option(gs_scene* scene, const char* key, int64_t value) {
 		scene->use_wavefront = value != 0;
 		return GS_OK;
 	}
+	if (std::strcmp(key, "wavefront_sort") == 0) { scene->wavefront_sort = value != 0; return GS_OK; }
 	if (std::strcmp(key, "pool_capacity") == 0) {
 		if (value < 128 || value > (1ll << 26)) return fail(GS_ERR_INVALID, "pool_capacity out of range");
 		scene->pool_capacity = (int)value;
@@ -195,12 +196,22 @@ static int render_wavefront(gs_scene* s, WavefrontParams& p, cudaStream_t st) {
 	p.pool.org = s->pool_org.p; p.pool.dir = s->pool_dir.p; p.pool.thr = s->pool_thr.p; p.pool.rad = s->pool_rad.p;
 	p.pool.ids = s->pool_ids.p; p.pool.hit = s->pool_hit.p; p.pool.n = n;
 	p.ctr = s->wave_ctr.p; p.free_list = s->free_list.p;
+	p.shade_queue = nullptr; p.shade_count = nullptr;
+	if (s->wavefront_sort) {
+		GS_CUDA(s->shade_queue.alloc((size_t)n * kShadeClasses, st)); GS_CUDA(s->shade_count.alloc(kShadeClasses, st));
+		p.shade_queue = s->shade_queue.p; p.shade_count = s->shade_count.p;
+	}
 	GS_CUDA(cudaMemsetAsync(p.ctr, 0, sizeof(WaveCounters), st));
 	const int kCheckEvery = 4;
 	for (int wave = 0;; ++wave) {
 		GS_CUDA(launch_wf_generate(p, wave == 0, st));
 		GS_CUDA(cudaMemsetAsync(&p.ctr->next_ray, 0, 2 * sizeof(unsigned), st));  // next_ray and n_free
 		GS_CUDA(launch_wf_traverse(p, s->sm_count, s->count_nodes, s->has_triangles, st));
+		if (p.shade_queue) {
+			GS_CUDA(cudaMemsetAsync(p.shade_count, 0, kShadeClasses * sizeof(unsigned), st));
+			GS_CUDA(launch_wf_classify(p, st));
+			s->launches += 1;
+		}
 		GS_CUDA(launch_wf_shade(p, st));
 		s->launches += 3;
 		if (wave % kCheckEvery == kCheckEvery - 1) {

@@ -144,6 +144,9 @@ struct gs_scene {
 	gs::DevBuf<float4> pool_thr, pool_rad;
 	gs::DevBuf<uint4> pool_ids, pool_hit;
 	gs::DevBuf<int> free_list;
+	gs::DevBuf<int> shade_queue;        // material-sorted shading queues (kShadeClasses x pool slots)
+	gs::DevBuf<unsigned> shade_count;
+	bool wavefront_sort = true;         // option "wavefront_sort"
 	gs::DevBuf<gs::WaveCounters> wave_ctr;
 	gs::WaveCounters* h_wave_ctr = nullptr;  // pinned
 

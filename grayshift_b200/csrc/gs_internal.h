@@ -92,10 +92,14 @@ struct WaveCounters {              // one small device struct per scene
 	int n_live;                    // slots holding a path
 };
 
+constexpr int kShadeClasses = 8;  // wavefront shading queues: miss, Lambertian (solid / textured), metal, glass, light, isotropic, spare
+
 struct WavefrontParams {
 	DeviceScene sc;
 	DCamera cam;
 	PathPool pool;
+	int* shade_queue;      // kShadeClasses segments of pool.n slots each: the rays of a wave sorted by shading class; nullptr = unsorted
+	unsigned* shade_count; // kShadeClasses counters
 	unsigned long long seed;
 	unsigned sample_begin, sample_count;
 	unsigned long long total_items;
@@ -107,6 +111,7 @@ struct WavefrontParams {
 
 cudaError_t launch_wf_generate(const WavefrontParams& p, bool first_wave, cudaStream_t stream);
 cudaError_t launch_wf_traverse(const WavefrontParams& p, int sm_count, bool count_nodes, bool triangles, cudaStream_t stream);
+cudaError_t launch_wf_classify(const WavefrontParams& p, cudaStream_t stream);
 cudaError_t launch_wf_shade(const WavefrontParams& p, cudaStream_t stream);
 
 }  // namespace gs

@@ -991,7 +991,7 @@ gs_scene::~gs_scene() {
 	cudaDeviceSynchronize();  // nothing of this scene is in flight when its memory goes back to the pool
 	cudaStream_t st = up;
 	pool_org.release(st); pool_dir.release(st); pool_thr.release(st); pool_rad.release(st); pool_ids.release(st); pool_hit.release(st);
-	free_list.release(st); wave_ctr.release(st);
+	free_list.release(st); wave_ctr.release(st); shade_queue.release(st); shade_count.release(st);
 	if (h_wave_ctr) cudaFreeHost(h_wave_ctr);
 	px_list[0].release(st); px_list[1].release(st); px_count.release(st); lum.release(st);
 	accum.release(st); out_rgb.release(st); out_counts.release(st); multi_landing.release(st);

@@ -9,8 +9,12 @@
 //   wf_generate_kernel  Camera::get_ray (camera.rs:204-226) for every free slot: path regeneration
 //   wf_traverse_kernel  ConstantMedium::hit + BVHNode/AABB/Sphere/Quad::hit (world.hit, camera.rs:177): persistent
 //                       warps that fetch the next ray the moment a lane finishes its ray (dynamic ray fetch)
-//   wf_shade_kernel     emitted + scatter + value_at + sample_background (camera.rs:178-201), accumulation of
-//                       finished paths (camera.rs:141), and the free list for the next generate
+//   wf_classify_kernel  material-sorted queue compaction: every traversed ray is filed under its shading class (miss, Lambertian
+//                       with a solid / another texture, metal, glass, light, isotropic) -- lanes of a warp that share a class
+//                       find each other with match.any, one atomic per class and warp reserves their places in the class's queue
+//   wf_shade_kernel     emitted + scatter + value_at + sample_background (camera.rs:178-201) over the queues, class by class
+//                       (a warp shades one material), accumulation of finished paths (camera.rs:141), and the free list for
+//                       the next generate
 //
 // A slot's path survives from wave to wave; the host launches waves until every (pixel, sample) item has been
 // started and the pool is empty.  Random numbers are the same Philox streams as in the megakernel and the oracle
@@ -135,15 +139,60 @@ __global__ void __launch_bounds__(kBlock) wf_traverse_kernel(const __grid_consta
 	flush_stats(P.stats, pc, 0u);
 }
 
+// ---- classify: material-sorted queue compaction -------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) wf_classify_kernel(const __grid_constant__ WavefrontParams P) {
+	const unsigned s = blockIdx.x * kBlock + threadIdx.x;
+	const unsigned lane = threadIdx.x & 31u;
+	int cls = -1;  // -1: nothing to shade in this slot
+	if (s < (unsigned)P.pool.n && (P.pool.ids[s].w & kSlotActive)) {
+		const uint4 hw = P.pool.hit[s];
+		if (hw.x == kNoHit && (int)hw.y < 0) cls = 0;  // miss: sample_background
+		else {
+			int mat;
+			if (hw.x != kNoHit) {
+				const uint32_t index = hw.x & kRefIndexMask, kind = hw.x >> kRefKindShift;
+				mat = kind == kKindQuad ? P.sc.quad_aux[index].x : (kind == kKindTriangle ? P.sc.tri_aux[index].x : P.sc.sph_aux[index].x);
+			} else mat = P.sc.media[hw.y].phase_mat;
+			const DMaterial m = P.sc.materials[mat];
+			if (m.kind == 0) cls = P.sc.textures[m.tex].kind == 0 ? 1 : 2;  // Lambertian: solid colour / checker, image, noise
+			else cls = 2 + m.kind;                                             // metal 3, dielectric 4, light 5, isotropic 6
+		}
+	}
+	const unsigned live = __ballot_sync(kFull, cls >= 0);
+	if (cls >= 0) {
+		const unsigned peers = __match_any_sync(live, cls);  // the lanes of this warp in the same class
+		const int leader = __ffs(peers) - 1;
+		unsigned base = 0;
+		if ((int)lane == leader) base = atomicAdd(P.shade_count + cls, (unsigned)__popc(peers));
+		base = __shfl_sync(peers, base, leader);
+		P.shade_queue[(size_t)cls * P.pool.n + base + __popc(peers & lanemask_lt())] = (int)s;
+	}
+}
+
 // ---- shade -----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBlock) wf_shade_kernel(const __grid_constant__ WavefrontParams P) {
 	__shared__ uint8_t s_perm[256];
 	load_perm(s_perm, P.sc.perlin_perm);
-	const unsigned s = blockIdx.x * kBlock + threadIdx.x;
+	unsigned s = blockIdx.x * kBlock + threadIdx.x;
 	const unsigned lane = threadIdx.x & 31u;
 	PathCounters pc = {0u, 0u, 0u};
 	bool terminated = false;
 	uint4 id = make_uint4(0u, 0u, 0u, 0u);
+	if (P.shade_queue) {
+		// thread i takes the i-th entry of the concatenated class queues; each class starts on a warp boundary, so a warp
+		// never mixes two classes
+		unsigned i = s, slot = 0xffffffffu;
+#pragma unroll
+		for (int c = 0; c < kShadeClasses; ++c) {
+			const unsigned n = P.shade_count[c], padded = (n + 31u) & ~31u;
+			if (slot == 0xffffffffu) {
+				if (i < n) slot = (unsigned)P.shade_queue[(size_t)c * P.pool.n + i];
+				else if (i < padded) slot = 0xfffffffeu;  // padding lane of this class's last warp
+				else i -= padded;
+			}
+		}
+		s = slot < 0xfffffffeu ? slot : (unsigned)P.pool.n;
+	}
 	if (s < (unsigned)P.pool.n) id = P.pool.ids[s];
 	if (id.w & kSlotActive) {
 		PathState st;
@@ -217,8 +266,15 @@ cudaError_t launch_wf_traverse(const WavefrontParams& p, int sm_count, bool coun
 	}
 }
 
+cudaError_t launch_wf_classify(const WavefrontParams& p, cudaStream_t stream) {
+	wf_classify_kernel<<<(p.pool.n + kBlock - 1) / kBlock, kBlock, 0, stream>>>(p);
+	return cudaGetLastError();
+}
+
 cudaError_t launch_wf_shade(const WavefrontParams& p, cudaStream_t stream) {
-	wf_shade_kernel<<<(p.pool.n + kBlock - 1) / kBlock, kBlock, 0, stream>>>(p);
+	// sorted: every class is padded to a whole warp, so up to kShadeClasses * 31 more threads than slots
+	const int threads = p.pool.n + (p.shade_queue ? kShadeClasses * 32 : 0);
+	wf_shade_kernel<<<(threads + kBlock - 1) / kBlock, kBlock, 0, stream>>>(p);
 	return cudaGetLastError();
 }
 

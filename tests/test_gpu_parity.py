@@ -348,14 +348,17 @@ def test_device_output_stage_matches_write_color():
     assert rgb8.max() == 255 and rgb8.min() >= 0   # the HDR sky saturates at 0.999 * 256 = 255
 
 
+@pytest.mark.parametrize("sort", [1, 0])
 @pytest.mark.parametrize("name,kw", [("c4", {"width": 200}), ("c1", {"width": 200}), ("scene7", {"width": 120})])
-def test_wavefront_pipeline_renders_the_same_image(name, kw):
-    """The optional wavefront pipeline (generate / traverse / shade over a path pool) uses the same Philox streams and
-    device functions as the megakernel: same samples, same image up to fp32 summation order."""
+def test_wavefront_pipeline_renders_the_same_image(name, kw, sort):
+    """The optional wavefront pipeline (generate / traverse / classify / shade over a path pool, the shading queues sorted by
+    material with warp match / ballot compaction, or unsorted) uses the same Philox streams and device functions as the
+    megakernel: same samples, same image up to fp32 summation order."""
     host = gs.HostScene.build(name, spp=16, **kw)
     dev = gs.DeviceScene(host)
     a, ca, sa = dev.render(seed=5)
     dev.set_option("wavefront", 1)
+    dev.set_option("wavefront_sort", sort)
     dev.set_option("pool_capacity", 20000)   # smaller than the image: slots are reused across waves
     b, cb, sb = dev.render(seed=5)
     assert np.array_equal(ca, cb) and sa.paths == sb.paths
