@@ -316,6 +316,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-extras", action="store_true", help="skip the config-5, strong-scaling and single-process extras")
     ap.add_argument("--bvh-width", type=int, default=0, choices=[0, 2, 8], help="0 = the library's choice by scene size")
+    ap.add_argument("--wavefront-sort", type=int, default=1, choices=[0, 1], help="wavefront pipeline: material-sorted shading queues")
     ap.add_argument("--pipeline", default="megakernel", choices=["megakernel", "wavefront"],
                     help="device pipeline (the megakernel is the default, chosen from ncu evidence; see DESIGN.md section 6)")
     args = ap.parse_args()
@@ -346,6 +347,7 @@ def main():
     flatten_s = time.perf_counter() - t0
     scene = gs.DeviceScene(host, device=local_rank)
     scene.set_option("wavefront", 1 if args.pipeline == "wavefront" else 0)
+    scene.set_option("wavefront_sort", args.wavefront_sort)
     if args.bvh_width:
         scene.set_option("bvh_width", args.bvh_width)
     W, H = scene.width, scene.height

@@ -14,6 +14,12 @@ timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; ech
 timeout 400 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; cut -c1-160 gpurun_out/bench_ref.json
 EXTRA="--no-extras" bash scripts/gpu_all_configs.sh > gpurun_out/all_configs.log 2>&1; tail -5 gpurun_out/all_configs.log
 CFGS="c4 c1 c3" bash scripts/gpu_ab.sh 2>&1 | tail -6
+# the wavefront alternative with and without its material-sorted shading queues
+: > gpurun_out/wavefront.jsonl
+for cfg in c4 c1 c3; do for srt in 1 0; do
+  timeout 300 python bench.py --config $cfg --steps 3 --warmup 2 --e2e-steps 1 --no-extras --no-cpu-baseline --pipeline wavefront --wavefront-sort $srt 2>/dev/null | tail -1 >> gpurun_out/wavefront.jsonl
+  python -c "import json;d=json.loads(open('gpurun_out/wavefront.jsonl').read().strip().split('\n')[-1]);print('wavefront $cfg sort=$srt', round(d['value']/1e6,1), 'M paths/s')"
+done; done
 GS_TRACE=1 timeout 600 python bench.py --config c5 --steps 2 --warmup 1 --e2e-steps 3 --no-extras --no-cpu-baseline 2> gpurun_out/b_c5.err | tail -1 > gpurun_out/c5.json
 grep -E "gs_scene_create|build_nodes" gpurun_out/b_c5.err | tail -13
 # ncu: launch list of a short default run, full captures of the dominant kernel on C4 and C5
