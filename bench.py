@@ -316,7 +316,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-extras", action="store_true", help="skip the config-5, strong-scaling and single-process extras")
     ap.add_argument("--bvh-width", type=int, default=0, choices=[0, 2, 8], help="0 = the library's choice by scene size")
-    ap.add_argument("--wavefront-sort", type=int, default=1, choices=[0, 1], help="wavefront pipeline: material-sorted shading queues")
+    ap.add_argument("--wavefront-sort", type=int, default=0, choices=[0, 1], help="wavefront pipeline: material-sorted shading queues")
     ap.add_argument("--pipeline", default="megakernel", choices=["megakernel", "wavefront"],
                     help="device pipeline (the megakernel is the default, chosen from ncu evidence; see DESIGN.md section 6)")
     args = ap.parse_args()
@@ -447,6 +447,25 @@ def main():
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = (n_px * spp_step * world * e2e_steps) / float(e2e_s.item())
 
+    # what the DEVICE actually fetches per ray (the HBM model above counts the reference's traversal): one short launch of the
+    # counting variant of the kernel -> node visits per ray x node size (64 B binary, 96 B eight-wide)
+    device_bytes = None
+    if rank == 0 and args.pipeline == "megakernel":
+        try:
+            scene.set_option("count_nodes", 1)
+            scene.stats()
+            probe = torch.zeros((n_px, 4), dtype=torch.float32, device=device)
+            scene.render_accumulate(probe.data_ptr(), seed=3, sample_begin=0, sample_count=max(1, min(8, spp_step)), stream=stream.cuda_stream)
+            torch.cuda.synchronize(device)
+            stp = scene.stats()
+            node_bytes = 96 if scene.info("bvh_width") == 8 else 64
+            device_bytes = {"node_visits_per_ray": stp.node_visits / max(1, stp.rays), "node_bytes": node_bytes,
+                            "node_bytes_per_ray": stp.node_visits / max(1, stp.rays) * node_bytes,
+                            "note": "fetched from L1/L2, not from HBM; leaf records (32 B sphere / 96 B quad per test) come on top"}
+            scene.set_option("count_nodes", 0)
+            del probe
+        except Exception as e:
+            device_bytes = {"error": str(e)[:200]}
     extra = {}
     if not args.no_extras:
         extra = run_extras(args, gs, gdist, dist, torch, np, scene, host, rank, local_rank, world, device, stream, barrier)
@@ -481,6 +500,8 @@ def main():
             "clocks": clk, "wall_s_timed_region": wall,
         }
         line["roofline"].update(issue_roofline(args.config))
+        if device_bytes:
+            line["roofline"]["device"] = device_bytes
         if extra:
             line["extra"] = extra
         if not args.no_cpu_baseline and world == 1:

@@ -73,7 +73,9 @@ constexpr int kCounterSlots = 64;
 constexpr size_t kSmallSceneBytes = 128u << 10;  // C1 (486 spheres) is 47 KB, C3 2 KB, C4 (the one that wants the spill-free build) 490 KB
 constexpr unsigned kAdaptiveTailPixels = 8192;   // adaptive renders: below this many unfinished pixels, switch to one warp per pixel (measured 256 / 2048 / 8192: profiles/r02_v2_adaptive_times.log)
 constexpr int kStatSlots = 16;                   // [0..3] = gs_stats totals; [4..] only written by the GS_DIVERGENCE_STATS diagnostic build
-constexpr size_t kWideMinPrims = 16384;          // scenes with at least this many primitives traverse the eight-wide tree (override: GS_BVH_WIDTH)
+constexpr size_t kWideMinPrims = 65536;          // scenes with at least this many primitives traverse the eight-wide tree (override: GS_BVH_WIDTH);
+                                                 // measured crossover on the sphere cloud: binary +9 % at 30 k, eight-wide +3 % at 100 k, +10 % at 300 k
+                                                 // (profiles/r02_v5_tree_threshold.log)
 
 }  // namespace gs
 
@@ -146,7 +148,7 @@ struct gs_scene {
 	gs::DevBuf<int> free_list;
 	gs::DevBuf<int> shade_queue;        // material-sorted shading queues (kShadeClasses x pool slots)
 	gs::DevBuf<unsigned> shade_count;
-	bool wavefront_sort = true;         // option "wavefront_sort"
+	bool wavefront_sort = false;        // option "wavefront_sort": measured 6...9 % slower than the unsorted queues (profiles/r02_v5_wavefront_sort.log)
 	gs::DevBuf<gs::WaveCounters> wave_ctr;
 	gs::WaveCounters* h_wave_ctr = nullptr;  // pinned
 

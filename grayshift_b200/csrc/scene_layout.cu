@@ -285,6 +285,7 @@ struct WideBuild {
 	std::vector<int> kids;        // 8 per wide node, ABI node index or -1
 	std::vector<int> child_base;  // wide index of the first internal kid
 	std::vector<int> of_bin;      // wide node -> the binary node it replaces
+	std::vector<size_t> level_begin;  // wide nodes of level l are [level_begin[l], level_begin[l + 1]) (breadth-first numbering)
 	int depth = 0;                // levels of the eight-wide tree
 	int binary_depth = 0;         // deepest node of the binary tree (root = 0)
 };
@@ -296,13 +297,15 @@ void build_wide_topology(const gs_bvh_node* N, size_t n_nodes, WideBuild& w) {
 		area[i] = (float)(dx * dy + dy * dz + dz * dx);
 	});
 	auto internal = [&](int a) { return N[a].ref_count == 0; };
+	// experiment knob: fewer children per node (the slots stay eight)
+	static const int arity = [] { const char* e = std::getenv("GS_WIDE_ARITY"); const int v = e ? std::atoi(e) : 8; return v < 2 ? 2 : (v > 8 ? 8 : v); }();
 	// one wide node: collapse + octant slots; returns the number of internal kids
 	// (depth_in = binary depth of node a; kid_depth[] = binary depths of the kids, in slot order)
 	auto make_node = [&](int a, int depth_in, int* slot_kid, int* slot_depth) -> int {
 		int kids[8] = {N[a].left, N[a].right, -1, -1, -1, -1, -1, -1};
 		int kd[8] = {depth_in + 1, depth_in + 1, 0, 0, 0, 0, 0, 0};
 		int n = 2;
-		while (n < 8) {
+		while (n < arity) {
 			int best = -1;
 			for (int k = 0; k < n; ++k)
 				if (internal(kids[k]) && (best < 0 || area[kids[k]] > area[kids[best]])) best = k;
@@ -345,6 +348,7 @@ void build_wide_topology(const gs_bvh_node* N, size_t n_nodes, WideBuild& w) {
 	size_t base = 0;
 	while (!level.empty()) {
 		const size_t L = level.size();
+		w.level_begin.push_back(base);
 		w.kids.resize((base + L) * 8);
 		w.child_base.resize(base + L);
 		w.of_bin.insert(w.of_bin.end(), level.begin(), level.end());
@@ -374,6 +378,7 @@ void build_wide_topology(const gs_bvh_node* N, size_t n_nodes, WideBuild& w) {
 		level_depth.swap(next_depth);
 		++w.depth;
 	}
+	w.level_begin.push_back(base);
 	w.binary_depth = deepest.load();
 }
 }  // namespace
@@ -503,7 +508,8 @@ int layout_scene(gs_scene* s, const gs_scene_desc* d) {
 		// own singles, own larger leaves, then the internal kids' subtrees in slot order
 		struct Tot { uint32_t prim[3], refs; };
 		std::vector<Tot> sub(nW), start(nW);
-		for (size_t h = nW; h-- > 0;) {
+		// (level by level: the nodes of a level only read the level below / write the level below, so each level is a parallel loop)
+		auto subtree_total = [&](size_t h) {
 			Tot t{{own[h].single[0] + own[h].multi[0], own[h].single[1] + own[h].multi[1], own[h].single[2] + own[h].multi[2]}, own[h].refs_single + own[h].refs_multi};
 			const int* kids = wb.kids.data() + 8 * h;
 			int rank = 0;
@@ -514,9 +520,8 @@ int layout_scene(gs_scene* s, const gs_scene_desc* d) {
 				t.refs += c.refs;
 			}
 			sub[h] = t;
-		}
-		start[0] = Tot{{0, 0, 0}, 0};
-		for (size_t h = 0; h < nW; ++h) {
+		};
+		auto place_children = [&](size_t h) {
 			Tot cur = start[h];
 			for (int x = 0; x < 3; ++x) cur.prim[x] += own[h].single[x] + own[h].multi[x];
 			cur.refs += own[h].refs_single + own[h].refs_multi;
@@ -529,6 +534,16 @@ int layout_scene(gs_scene* s, const gs_scene_desc* d) {
 				for (int x = 0; x < 3; ++x) cur.prim[x] += sub[c].prim[x];
 				cur.refs += sub[c].refs;
 			}
+		};
+		const size_t n_levels = wb.level_begin.size() - 1;
+		for (size_t l = n_levels; l-- > 0;) {
+			const size_t lo = wb.level_begin[l], cnt = wb.level_begin[l + 1] - lo;
+			parallel_for(cnt, [&](size_t i) { subtree_total(lo + i); }, 4096);
+		}
+		start[0] = Tot{{0, 0, 0}, 0};
+		for (size_t l = 0; l < n_levels; ++l) {
+			const size_t lo = wb.level_begin[l], cnt = wb.level_begin[l + 1] - lo;
+			parallel_for(cnt, [&](size_t i) { place_children(lo + i); }, 4096);
 		}
 		lap("  order: subtree offsets");
 		sph_src.assign(d->n_spheres, 0); quad_src.assign(d->n_quads, 0); tri_src.assign(d->n_triangles, 0);
@@ -637,6 +652,9 @@ int layout_scene(gs_scene* s, const gs_scene_desc* d) {
 	}
 	const size_t o_counters = section(kCounterSlots * sizeof(unsigned long long)), o_stats = section(kStatSlots * sizeof(unsigned long long));
 
+	if (trace_enabled())
+		std::fprintf(stderr, "[gs_scene_create] blob %zu B: refs %zu, spheres %zu (+path %d, +uvrot %d), quads %zu, tris %zu, images %zu, nodes in %zu\n", total,
+		             refs.size(), nS, (int)any_moving, (int)any_rot, nQ, nT, (size_t)d->n_images, nN);
 	Staging stg;
 	GS_CUDA(staging_acquire(total, stg));
 	struct StageGuard { Staging& g; cudaEvent_t ev = nullptr; ~StageGuard() { staging_release(g, ev); } } stage_guard{stg};

@@ -274,7 +274,7 @@ int gs_render_adaptive_accumulate(gs_scene* scene, const gs_camera* camera, cons
                                   void* cuda_stream);
 /* Options: "count_nodes" (0/1) switches to the kernel variant that counts BVH node fetches and texel reads;
  * "wavefront" (0/1) selects the wavefront pipeline for fixed-count renders; "pool_capacity" its path pool size;
- * "wavefront_sort" (0/1, default 1) its material-sorted shading queues;
+ * "wavefront_sort" (0/1, default 0) its material-sorted shading queues;
  * "bvh_width" (2 or 8) selects the tree the kernels traverse -- the binary tree or the eight-wide compressed tree
  * the library derives from it (default: by scene size; the other tree is built on first request). */
 int gs_scene_set_option(gs_scene* scene, const char* key, int64_t value);

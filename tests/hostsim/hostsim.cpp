@@ -28,6 +28,7 @@ int hs_scene_create(const gs_scene_desc* d, int width, gs_scene** out) {
 void hs_scene_destroy(gs_scene* s) { delete s; }
 int hs_scene_info(gs_scene* s, int64_t* out) {  // nodes2, nodes8, wide_depth, any leaf links
 	out[0] = (int64_t)s->h_bfs.size(); out[1] = (int64_t)s->w_child_base.size(); out[2] = s->wide_depth; out[3] = s->leaf_links8 != nullptr;
+	out[4] = (int64_t)s->blob_bytes; out[5] = (int64_t)s->h2d_bytes; out[6] = (int64_t)s->n_dnodes; out[7] = (int64_t)s->n_dnodes8;
 	return 0;
 }
 

@@ -44,9 +44,9 @@ class SimScene:
         self.h = h
 
     def info(self):
-        out = (C.c_int64 * 4)()
+        out = (C.c_int64 * 8)()
         self.L.hs_scene_info(self.h, out)
-        return dict(nodes2=out[0], nodes8=out[1], wide_depth=out[2], links=out[3])
+        return dict(nodes2=out[0], nodes8=out[1], wide_depth=out[2], links=out[3], blob_bytes=out[4], h2d_bytes=out[5], n_dnodes=out[6], n_dnodes8=out[7])
 
     def trace(self, rays, tmin=0.001, tmax=1.7976931348623157e308):
         rays = np.ascontiguousarray(rays, dtype=np.float64)
