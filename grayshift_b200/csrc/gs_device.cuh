@@ -118,6 +118,7 @@ struct DeviceScene {
 	const uint8_t* perlin_perm;
 	int n_media;
 	int root;  // node index or leaf code
+	uint32_t prmt_hi;  // 0x47000000, passed as DATA so that the compiler keeps it in a register (see Trav8::qf)
 };
 
 struct DCamera {
@@ -456,6 +457,9 @@ __device__ __forceinline__ void leaf_intersect(const DeviceScene& sc, const Ray&
 // ==========================================================================================
 // Traversal policy 1: the binary tree (DNode).  State = (node, sp) + the per-thread stack of links.
 // ==========================================================================================
+#ifndef GS_PRMT_IMM
+#define GS_PRMT_IMM 1  // eight-wide node test: PRMT selectors as immediates (0 = leave the operand choice to the compiler)
+#endif
 #ifndef GS_POP_CULL
 #define GS_POP_CULL 0  // binary tree: push the far child's entry distance with its link and drop it at pop time if the closest hit
                        // has come nearer since (host simulation: 32...48 % of the pops are stale on C1 / C4 / C5, each one a wasted node
@@ -630,8 +634,21 @@ struct Trav8 {
 	}
 
 	// 32768 + q as a float: byte q goes to mantissa bits 8..15 of 0x47000000 (one PRMT, no integer-to-float conversion)
-	__device__ __forceinline__ static float qf(uint32_t word, int j) {
+	// The selector is written as an immediate and the constant kept in a register (`k47`, read from DeviceScene::prmt_hi so that
+	// the compiler cannot fold it): PRMT has one immediate slot, and left alone ptxas gives it to the constant and spends a MOV per PRMT on
+	// the selector -- 48 extra instructions per node.
+	__device__ __forceinline__ static float qf(uint32_t word, int j, uint32_t k47) {
+#if GS_PRMT_IMM && defined(__CUDA_ARCH__)
+		uint32_t d;
+		if (j == 0) asm("prmt.b32 %0, %1, %2, 0x7404;" : "=r"(d) : "r"(word), "r"(k47));
+		else if (j == 1) asm("prmt.b32 %0, %1, %2, 0x7414;" : "=r"(d) : "r"(word), "r"(k47));
+		else if (j == 2) asm("prmt.b32 %0, %1, %2, 0x7424;" : "=r"(d) : "r"(word), "r"(k47));
+		else asm("prmt.b32 %0, %1, %2, 0x7434;" : "=r"(d) : "r"(word), "r"(k47));
+		return __uint_as_float(d);
+#else
+		(void)k47;
 		return __uint_as_float(__byte_perm(word, 0x47000000u, j == 0 ? 0x7404 : (j == 1 ? 0x7414 : (j == 2 ? 0x7424 : 0x7434))));
+#endif
 	}
 
 	// Visit the nearest unvisited member of the current group: fetch it, test its eight children's boxes, and make their
@@ -663,11 +680,12 @@ struct Trav8 {
 		const uint32_t neary[2] = {ny ? qy.z : qy.x, ny ? qy.w : qy.y}, fary[2] = {ny ? qy.x : qy.z, ny ? qy.y : qy.w};
 		const uint32_t nearz[2] = {nz ? qz.z : qz.x, nz ? qz.w : qz.y}, farz[2] = {nz ? qz.x : qz.z, nz ? qz.y : qz.w};
 		uint32_t hits = 0u;  // slot order
+		const uint32_t k47 = GS_PRMT_IMM ? sc.prmt_hi : 0x47000000u;
 #pragma unroll
 		for (int k = 0; k < 8; ++k) {
 			const int w = k >> 2, j = k & 3;
-			const float en = fmaxf(fmaxf(fmaf(qf(nearx[w], j), ax, bx), fmaf(qf(neary[w], j), ay, by)), fmaxf(fmaf(qf(nearz[w], j), az, bz), 0.0f));
-			const float ex = fminf(fminf(fmaf(qf(farx[w], j), ax, bx), fmaf(qf(fary[w], j), ay, by)), fminf(fmaf(qf(farz[w], j), az, bz), rc.tmax32));
+			const float en = fmaxf(fmaxf(fmaf(qf(nearx[w], j, k47), ax, bx), fmaf(qf(neary[w], j, k47), ay, by)), fmaxf(fmaf(qf(nearz[w], j, k47), az, bz), 0.0f));
+			const float ex = fminf(fminf(fmaf(qf(farx[w], j, k47), ax, bx), fmaf(qf(fary[w], j, k47), ay, by)), fminf(fmaf(qf(farz[w], j, k47), az, bz), rc.tmax32));
 			if (en <= ex) hits |= 1u << k;
 		}
 		// internal hits to the low byte, leaf hits to the third byte, then slot k -> bit (k ^ octinv) in both at once

@@ -5,6 +5,7 @@
 #include <memory>
 #include <string>
 #include <thread>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/grayshift.h"
@@ -22,17 +23,20 @@ int fail(int code, const std::string& msg);
 // Independent iterations over the host threads (scene creation of a 10^6-primitive scene spends its time in such loops);
 // small ranges stay on the calling thread.
 unsigned host_threads();
+// (a process-wide pool of worker threads that sleep between loops: a scene creation runs some thirty of these loops, and
+// starting and joining sixteen threads for each was a tenth of its time).  pool_run hands out [0, n) in pieces of `grain`;
+// the caller takes part; a loop started while the pool is busy -- from another host thread, or from inside a loop body --
+// simply runs on its own thread.
+void pool_run(size_t n, size_t grain, void (*fn)(void* ctx, size_t lo, size_t hi), void* ctx);
 template <class F> void parallel_for(size_t n, F&& body, size_t serial_below = 32768) {
 	const unsigned threads = host_threads();
 	if (n < serial_below || threads < 2) { for (size_t i = 0; i < n; ++i) body(i); return; }
-	std::vector<std::thread> pool;
-	const size_t chunk = (n + threads - 1) / threads;
-	for (unsigned t = 0; t < threads; ++t) {
-		const size_t lo = (size_t)t * chunk, hi = lo + chunk < n ? lo + chunk : n;
-		if (lo >= hi) break;
-		pool.emplace_back([lo, hi, &body]() { for (size_t i = lo; i < hi; ++i) body(i); });
-	}
-	for (auto& th : pool) th.join();
+	using Body = typename std::remove_reference<F>::type;
+	size_t grain = n / ((size_t)threads * 8);
+	if (grain < serial_below / 16) grain = serial_below / 16;
+	if (grain < 1) grain = 1;
+	pool_run(n, grain, [](void* ctx, size_t lo, size_t hi) { Body& b = *static_cast<Body*>(ctx); for (size_t i = lo; i < hi; ++i) b(i); },
+	         const_cast<void*>(static_cast<const void*>(&body)));
 }
 
 // Device memory comes from the device's stream-ordered pool with the release threshold lifted, so creating and
@@ -100,6 +104,7 @@ struct gs_scene {
 	std::vector<int> w_kids;
 	std::vector<int> w_child_base;
 	std::vector<uint32_t> w_prim_base;
+	bool w_any_link = false;  // some leaf cannot be addressed as base + offset from its wide node (build_nodes8 then emits the side table)
 	std::unique_ptr<int[]> h_leaf_direct;  // ABI leaf -> device primitive index if the leaf is one freshly placed primitive the wide node can address by offset, else -1
 	int wide_depth = 0;
 	double origin_limit = 0.0;

@@ -50,6 +50,10 @@ enum LaneState : int { kDead = 0, kTraverse = 1, kShade = 2, kSetup = 3 };
 #endif
 constexpr int kTopNodes = GS_TOP_SMEM;
 static_assert(kTopNodes <= kNodePad, "gs_scene_create pads the node array to kNodePad entries");
+#ifndef GS_MIN_SHADE_WIDE
+#define GS_MIN_SHADE_WIDE 20  // the same threshold in the kernels that walk the eight-wide tree: a wide node step costs three times a binary one,
+                              // so waiting for the 24th ray is dearer there (16 / 20 / 24: 386.9 / 388.4 / 377.2 M paths/s on config 5, profiles/r02_v6_variants.log)
+#endif
 #ifndef GS_BAIL
 #define GS_BAIL 6         // resumable traversal: the node loop of a round ends once no more than this many lanes still descend
 #endif
@@ -262,7 +266,8 @@ __global__ void __launch_bounds__(kBlock, (kF & 8) ? GS_MIN_BLOCKS + 1 : GS_MIN_
 		//   * runs the leaf code once kLeafT lanes wait on a leaf (or nobody can step).
 		// (Lanes without a ray at entry -- only at the very end of the image -- do not count as finished: with fewer than
 		// kMinShade rays in the warp, all of them run to completion.)
-		const int n_trav0 = __popc(trav0), exit_at = n_trav0 < kMinShade ? n_trav0 : kMinShade;
+		constexpr int kExit = (kF & 16) ? GS_MIN_SHADE_WIDE : kMinShade;
+		const int n_trav0 = __popc(trav0), exit_at = n_trav0 < kExit ? n_trav0 : kExit;
 		const bool trav = state == kTraverse;
 		for (;;) {
 			// node phase: the classic tight per-lane loop, except that the lanes still descending give up once no more than

@@ -12,8 +12,10 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <condition_variable>
 #include <cstring>
 #include <mutex>
+#include <pthread.h>
 
 #include "gs_host.h"
 
@@ -32,6 +34,84 @@ unsigned host_threads() {
 		return t > 32u ? 32u : (t ? t : 1u);
 	}();
 	return n;
+}
+
+// ---- the worker pool behind parallel_for --------------------------------------------------------------------
+namespace {
+class HostPool {
+public:
+	explicit HostPool(unsigned helpers) {
+		for (unsigned i = 0; i < helpers; ++i) workers_.emplace_back([this] { work(); });
+	}
+	~HostPool() {
+		{ std::lock_guard<std::mutex> lk(m_); stop_ = true; ++generation_; }
+		wake_.notify_all();
+		for (auto& t : workers_) t.join();
+	}
+	// false: busy (another loop is running), the caller should run its loop itself
+	bool run(size_t n, size_t grain, void (*fn)(void*, size_t, size_t), void* ctx) {
+		std::unique_lock<std::mutex> busy(busy_, std::try_to_lock);
+		if (!busy.owns_lock()) return false;
+		{
+			std::lock_guard<std::mutex> lk(m_);
+			fn_ = fn; ctx_ = ctx; n_ = n; grain_ = grain;
+			next_.store(0, std::memory_order_relaxed);
+			pending_ = (unsigned)workers_.size();
+			++generation_;
+		}
+		wake_.notify_all();
+		drain();
+		std::unique_lock<std::mutex> lk(m_);
+		done_.wait(lk, [this] { return pending_ == 0; });
+		return true;
+	}
+
+private:
+	void drain() {
+		for (;;) {
+			const size_t lo = next_.fetch_add(grain_, std::memory_order_relaxed);
+			if (lo >= n_) break;
+			fn_(ctx_, lo, lo + grain_ < n_ ? lo + grain_ : n_);
+		}
+	}
+	void work() {
+		uint64_t seen = 0;
+		for (;;) {
+			{
+				std::unique_lock<std::mutex> lk(m_);
+				wake_.wait(lk, [&] { return generation_ != seen; });
+				seen = generation_;
+				if (stop_) return;
+			}
+			drain();
+			{
+				std::lock_guard<std::mutex> lk(m_);
+				if (--pending_ == 0) done_.notify_one();
+			}
+		}
+	}
+	std::vector<std::thread> workers_;
+	std::mutex m_, busy_;
+	std::condition_variable wake_, done_;
+	uint64_t generation_ = 0;
+	bool stop_ = false;
+	unsigned pending_ = 0;
+	void (*fn_)(void*, size_t, size_t) = nullptr;
+	void* ctx_ = nullptr;
+	size_t n_ = 0, grain_ = 1;
+	std::atomic<size_t> next_{0};
+};
+}  // namespace
+
+namespace { std::atomic<bool> g_forked{false}; }
+void pool_run(size_t n, size_t grain, void (*fn)(void*, size_t, size_t), void* ctx) {
+	// Never destroyed: its threads sleep on its condition variable until the process ends.  A forked child has the object
+	// but not the threads, and runs its loops on the calling thread.
+	static HostPool* const pool = [] {
+		pthread_atfork(nullptr, nullptr, [] { g_forked.store(true); });
+		return new HostPool(host_threads() - 1);  // host_threads() >= 2 here (parallel_for runs small or single-threaded loops itself)
+	}();
+	if (g_forked.load(std::memory_order_relaxed) || !pool->run(n, grain, fn, ctx)) fn(ctx, 0, n);
 }
 
 cudaError_t dev_alloc(void** p, size_t bytes, cudaStream_t stream) {
@@ -113,8 +193,18 @@ void staging_forget_event(cudaEvent_t ev) {
 
 namespace {
 
-float float_down(double x) { float f = (float)x; if ((double)f > x) f = std::nextafterf(f, -INFINITY); return f; }
-float float_up(double x) { float f = (float)x; if ((double)f < x) f = std::nextafterf(f, INFINITY); return f; }
+// the neighbouring floats of a FINITE float, on the bit pattern (std::nextafterf is a library call, and the node builders
+// round some ten million box planes outward per scene)
+inline float next_below(float f) {
+	uint32_t u; std::memcpy(&u, &f, 4);
+	if ((u << 1) == 0u) u = 0x80000001u;      // +-0 -> the smallest negative subnormal
+	else if (u >> 31) ++u;                      // negative: away from zero
+	else --u;                                   // positive: towards zero
+	std::memcpy(&f, &u, 4); return f;
+}
+inline float next_above(float f) { return -next_below(-f); }
+float float_down(double x) { float f = (float)x; if ((double)f > x) f = std::isfinite(f) ? next_below(f) : std::nextafterf(f, -INFINITY); return f; }
+float float_up(double x) { float f = (float)x; if ((double)f < x) f = std::isfinite(f) ? next_above(f) : std::nextafterf(f, INFINITY); return f; }
 bool finite3(const double* v) { return std::isfinite(v[0]) && std::isfinite(v[1]) && std::isfinite(v[2]); }
 
 DSphere make_dsphere(const gs_sphere& s) {
@@ -164,6 +254,15 @@ template <class F> long first_bad(size_t n, F&& bad) {
 	return worst.load();
 }
 
+// Per-sphere flags (bit 0 moving, bit 1 baked with a RotateY) gathered by validate_desc's pass over the sphere array and
+// used by layout_scene on the same thread right after: a compact table the layout can index at random without touching
+// the 100-byte sphere records again.  Keyed by the array it was made from; layout_scene rebuilds it if the key differs.
+thread_local std::vector<uint8_t> t_sphere_flags;
+thread_local const gs_sphere* t_sphere_flags_of = nullptr;
+inline uint8_t sphere_flags_of(const gs_sphere& s) {
+	return (uint8_t)((s.moving ? 1 : 0) | ((s.uv_rotation[0] != 1.0 || s.uv_rotation[1] != 0.0) ? 2 : 0));
+}
+
 bool trace_enabled() { static const bool t = std::getenv("GS_TRACE") != nullptr; return t; }
 struct Lap {
 	const char* who;
@@ -181,6 +280,7 @@ struct Lap {
 
 // ---- validation: nothing aborts across the boundary, so everything the layout and the kernels index is checked here ----
 int validate_desc(const gs_scene_desc* d) {
+	Lap lap("validate_desc");
 	if (!d) return fail(GS_ERR_INVALID, "null scene description");
 	if (d->abi_version != GS_ABI_VERSION) return fail(GS_ERR_INVALID, "abi_version mismatch");
 	if (d->n_spheres + d->n_quads + d->n_triangles == 0) return fail(GS_ERR_INVALID, "empty scene (the reference recurses forever on an empty list, BVH.rs:18-65)");
@@ -201,8 +301,12 @@ int validate_desc(const gs_scene_desc* d) {
 	if (d->n_images && !d->images) return fail(GS_ERR_INVALID, "null image array");
 	auto bad_mat = [&](int m) { return m < 0 || (size_t)m >= d->n_materials; };
 	long b;
+	t_sphere_flags.resize(d->n_spheres);
+	t_sphere_flags_of = d->spheres;
+	uint8_t* sphere_flags = t_sphere_flags.data();
 	b = first_bad(d->n_spheres, [&](size_t i) {
 		const gs_sphere& s = d->spheres[i];
+		sphere_flags[i] = sphere_flags_of(s);
 		return !finite3(s.center) || !finite3(s.path) || !std::isfinite(s.radius) || s.radius == 0.0 || !std::isfinite(s.uv_rotation[0]) || !std::isfinite(s.uv_rotation[1]) || bad_mat(s.material);
 	});
 	if (b >= 0) return fail(GS_ERR_INVALID, "sphere " + std::to_string(b) + ": non-finite, zero radius or bad material index");
@@ -226,23 +330,29 @@ int validate_desc(const gs_scene_desc* d) {
 		if (!(m.density != 0.0) || !std::isfinite(m.density)) return fail(GS_ERR_INVALID, "medium: bad density");
 		if (bad_mat(m.phase_material)) return fail(GS_ERR_INVALID, "medium: bad phase material");
 	}
-	for (size_t i = 0; i < d->n_materials; ++i) {
+	// (one material and one texture per sphere is a common way to build a scene: these tables can have 10^6 rows)
+	auto material_fault = [&](size_t i) -> int {
 		const gs_material& m = d->materials[i];
-		if (m.kind < 0 || m.kind > GS_MAT_ISOTROPIC) return fail(GS_ERR_INVALID, "material " + std::to_string(i) + ": bad kind");
-		bool needs_tex = m.kind == GS_MAT_LAMBERTIAN || m.kind == GS_MAT_DIFFUSE_LIGHT || m.kind == GS_MAT_ISOTROPIC;
-		if (needs_tex && (m.texture < 0 || (size_t)m.texture >= d->n_textures)) return fail(GS_ERR_INVALID, "material " + std::to_string(i) + ": bad texture index");
-	}
-	for (size_t i = 0; i < d->n_textures; ++i) {
+		if (m.kind < 0 || m.kind > GS_MAT_ISOTROPIC) return 1;
+		const bool needs_tex = m.kind == GS_MAT_LAMBERTIAN || m.kind == GS_MAT_DIFFUSE_LIGHT || m.kind == GS_MAT_ISOTROPIC;
+		if (needs_tex && (m.texture < 0 || (size_t)m.texture >= d->n_textures)) return 2;
+		return 0;
+	};
+	b = first_bad(d->n_materials, [&](size_t i) { return material_fault(i) != 0; });
+	if (b >= 0) return fail(GS_ERR_INVALID, "material " + std::to_string(b) + (material_fault((size_t)b) == 1 ? ": bad kind" : ": bad texture index"));
+	auto texture_fault = [&](size_t i) -> int {
 		const gs_texture& t = d->textures[i];
-		if (t.kind < 0 || t.kind > GS_TEX_NOISE) return fail(GS_ERR_INVALID, "texture: bad kind");
-		if (t.kind == GS_TEX_CHECKER) {
-			// children must come earlier in the table: rules out cycles (Arc graphs are acyclic)
-			if (t.a < 0 || t.b < 0 || (size_t)t.a >= i || (size_t)t.b >= i) return fail(GS_ERR_INVALID, "checker texture " + std::to_string(i) + ": children must precede it");
-		}
-		if (t.kind == GS_TEX_IMAGE) {
-			if (t.a < 0 || (size_t)t.a >= d->n_images || d->images[t.a].format != GS_IMG_U8_RGB) return fail(GS_ERR_INVALID, "image texture: bad image index/format");
-		}
-		if (t.kind == GS_TEX_NOISE && !d->perlin_perm) return fail(GS_ERR_INVALID, "noise texture without perlin_perm");
+		if (t.kind < 0 || t.kind > GS_TEX_NOISE) return 1;
+		// children must come earlier in the table: rules out cycles (Arc graphs are acyclic)
+		if (t.kind == GS_TEX_CHECKER && (t.a < 0 || t.b < 0 || (size_t)t.a >= i || (size_t)t.b >= i)) return 2;
+		if (t.kind == GS_TEX_IMAGE && (t.a < 0 || (size_t)t.a >= d->n_images || d->images[t.a].format != GS_IMG_U8_RGB)) return 3;
+		if (t.kind == GS_TEX_NOISE && !d->perlin_perm) return 4;
+		return 0;
+	};
+	b = first_bad(d->n_textures, [&](size_t i) { return texture_fault(i) != 0; });
+	if (b >= 0) {
+		static const char* msg[] = {"", "texture: bad kind", "checker texture: children must precede it", "image texture: bad image index/format", "noise texture without perlin_perm"};
+		return fail(GS_ERR_INVALID, std::string(msg[texture_fault((size_t)b)]) + " (texture " + std::to_string(b) + ")");
 	}
 	for (size_t i = 0; i < d->n_images; ++i) {
 		const gs_image& im = d->images[i];
@@ -271,6 +381,7 @@ int validate_desc(const gs_scene_desc* d) {
 		return kind > 2 || (kind == 0 && idx >= d->n_spheres) || (kind == 1 && idx >= d->n_quads) || (kind == 2 && idx >= d->n_triangles);
 	});
 	if (b >= 0) return fail(GS_ERR_INVALID, "bad primitive reference " + std::to_string(b));
+	lap("all checks");
 	return GS_OK;
 }
 
@@ -291,11 +402,16 @@ struct WideBuild {
 };
 
 void build_wide_topology(const gs_bvh_node* N, size_t n_nodes, WideBuild& w) {
-	std::vector<float> area(n_nodes);
-	parallel_for(n_nodes, [&](size_t i) {
-		const double dx = N[i].bounds_max[0] - N[i].bounds_min[0], dy = N[i].bounds_max[1] - N[i].bounds_min[1], dz = N[i].bounds_max[2] - N[i].bounds_min[2];
-		area[i] = (float)(dx * dy + dy * dz + dz * dx);
-	});
+	// surface measure of a node's box, from the node record itself (a separate area array would be one more cache miss per
+	// candidate: this pass is bound by the latency of its scattered reads of the 2 * n_prims node records)
+	auto area_of = [&](int a) {
+		const double dx = N[a].bounds_max[0] - N[a].bounds_min[0], dy = N[a].bounds_max[1] - N[a].bounds_min[1], dz = N[a].bounds_max[2] - N[a].bounds_min[2];
+		return (float)(dx * dy + dy * dz + dz * dx);
+	};
+	auto prefetch_node = [&](int a) {
+		const char* p = reinterpret_cast<const char*>(N + a);
+		__builtin_prefetch(p); __builtin_prefetch(p + sizeof(gs_bvh_node) - 1);
+	};
 	auto internal = [&](int a) { return N[a].ref_count == 0; };
 	// experiment knob: fewer children per node (the slots stay eight)
 	static const int arity = [] { const char* e = std::getenv("GS_WIDE_ARITY"); const int v = e ? std::atoi(e) : 8; return v < 2 ? 2 : (v > 8 ? 8 : v); }();
@@ -304,16 +420,25 @@ void build_wide_topology(const gs_bvh_node* N, size_t n_nodes, WideBuild& w) {
 	auto make_node = [&](int a, int depth_in, int* slot_kid, int* slot_depth) -> int {
 		int kids[8] = {N[a].left, N[a].right, -1, -1, -1, -1, -1, -1};
 		int kd[8] = {depth_in + 1, depth_in + 1, 0, 0, 0, 0, 0, 0};
+		float ka[8];  // area of an internal kid, -1 for a leaf (never opened)
+		auto note = [&](int k) {
+			const int c = kids[k];
+			if (internal(c)) { ka[k] = area_of(c); prefetch_node(N[c].left); prefetch_node(N[c].right); }
+			else ka[k] = -1.0f;
+		};
+		prefetch_node(kids[0]); prefetch_node(kids[1]);
+		note(0); note(1);
 		int n = 2;
 		while (n < arity) {
 			int best = -1;
 			for (int k = 0; k < n; ++k)
-				if (internal(kids[k]) && (best < 0 || area[kids[k]] > area[kids[best]])) best = k;
+				if (ka[k] >= 0.0f && (best < 0 || ka[k] > ka[best])) best = k;
 			if (best < 0) break;
 			const int c = kids[best];
 			kids[best] = N[c].left;
 			kids[n] = N[c].right;
 			kd[best] += 1; kd[n] = kd[best];
+			note(best); note(n);
 			++n;
 		}
 		double centre[3];
@@ -325,17 +450,27 @@ void build_wide_topology(const gs_bvh_node* N, size_t n_nodes, WideBuild& w) {
 			for (int s = 0; s < 8; ++s) score[k][s] = ((s & 1) ? rel[0] : -rel[0]) + ((s & 2) ? rel[1] : -rel[1]) + ((s & 4) ? rel[2] : -rel[2]);
 		}
 		for (int s = 0; s < 8; ++s) slot_kid[s] = -1;
-		bool placed[8] = {false, false, false, false, false, false, false, false};
-		for (int round = 0; round < n; ++round) {
-			int bk = -1, bs = -1;
-			for (int k = 0; k < n; ++k) {
-				if (placed[k]) continue;
-				for (int s = 0; s < 8; ++s)
-					if (slot_kid[s] < 0 && (bk < 0 || score[k][s] > score[bk][bs])) { bk = k; bs = s; }
-			}
+		// greedy assignment: repeatedly the best (kid, free slot) pair, ties to the lowest kid and then the lowest slot.
+		// Each unplaced kid remembers its best free slot; only the kids that lose theirs look again.
+		int best_slot[8];
+		auto find_slot = [&](int k) {
+			int bs = -1;
+			for (int s = 0; s < 8; ++s)
+				if (slot_kid[s] < 0 && (bs < 0 || score[k][s] > score[k][bs])) bs = s;
+			best_slot[k] = bs;
+		};
+		for (int k = 0; k < n; ++k) find_slot(k);
+		uint32_t unplaced = (1u << n) - 1u;
+		while (unplaced) {
+			int bk = -1;
+			for (int k = 0; k < n; ++k)
+				if ((unplaced >> k & 1u) && (bk < 0 || score[k][best_slot[k]] > score[bk][best_slot[bk]])) bk = k;
+			const int bs = best_slot[bk];
 			slot_kid[bs] = kids[bk];
 			slot_depth[bs] = kd[bk];
-			placed[bk] = true;
+			unplaced &= ~(1u << bk);
+			for (int k = 0; k < n; ++k)
+				if ((unplaced >> k & 1u) && best_slot[k] == bs) find_slot(k);
 		}
 		int n_int = 0;
 		for (int s = 0; s < 8; ++s) if (slot_kid[s] >= 0 && internal(slot_kid[s])) ++n_int;
@@ -355,6 +490,8 @@ void build_wide_topology(const gs_bvh_node* N, size_t n_nodes, WideBuild& w) {
 		n_int.assign(L, 0);
 		kid_depth.assign(L * 8, 0);
 		parallel_for(L, [&](size_t i) {
+			if (i + 8 < L) prefetch_node(level[i + 8]);
+			if (i + 4 < L) { const gs_bvh_node& f = N[level[i + 4]]; prefetch_node(f.left); prefetch_node(f.right); }  // every level entry is internal
 			n_int[i] = make_node(level[i], level_depth[i], w.kids.data() + (base + i) * 8, kid_depth.data() + i * 8);
 			int m = 0;
 			for (int s = 0; s < 8; ++s) m = std::max(m, kid_depth[i * 8 + s]);
@@ -437,6 +574,14 @@ int layout_scene(gs_scene* s, const gs_scene_desc* d) {
 	s->h_leaf_direct.reset(new int[nN]);
 	s->w_prim_base.assign(nW * 3, 0u);
 	bool any_moving = false, any_rot = false;
+	std::atomic<bool> link_seen{false};
+	if (t_sphere_flags_of != d->spheres || t_sphere_flags.size() != d->n_spheres) {  // not reached through gs_scene_create, which validates first
+		t_sphere_flags.resize(d->n_spheres);
+		uint8_t* f = t_sphere_flags.data();
+		parallel_for(d->n_spheres, [&](size_t i) { f[i] = sphere_flags_of(d->spheres[i]); });
+		t_sphere_flags_of = d->spheres;
+	}
+	const uint8_t* sflag = t_sphere_flags.data();
 	auto emit_leaf = [&](int leaf) {
 		const gs_bvh_node& nd = N[leaf];
 		const uint32_t first = (uint32_t)refs.size();
@@ -445,7 +590,7 @@ int layout_scene(gs_scene* s, const gs_scene_desc* d) {
 			const uint32_t r = d->prim_refs[nd.first_ref + k], kind = r >> 30, idx = r & kRefIndexMask;
 			if (kind == 0) {
 				if (sph_new[idx] < 0) { sph_new[idx] = (int)sph_src.size(); sph_src.push_back((int)idx); fresh = true; }
-				const bool moving = d->spheres[idx].moving != 0;
+				const bool moving = (sflag[idx] & 1) != 0;
 				any_moving |= moving;
 				refs.push_back(((moving ? kKindMovingSphere : kKindSphere) << kRefKindShift) | (uint32_t)sph_new[idx]);
 			} else if (kind == 1) {
@@ -464,6 +609,7 @@ int layout_scene(gs_scene* s, const gs_scene_desc* d) {
 			s->h_leaf_code[leaf] = leaf_code((kind << 25) | idx, 0u);
 			if (fresh && kind != kKindMovingSphere) s->h_leaf_direct[leaf] = (int)idx;
 		}
+		if (s->h_leaf_direct[leaf] < 0) link_seen.store(true, std::memory_order_relaxed);
 	};
 	// Does every primitive sit in exactly one leaf?  (True for any tree without spatial splits.)  Then the order below can be
 	// computed from subtree sizes and filled by all host threads; otherwise the serial walk with its "seen before" test.
@@ -554,6 +700,8 @@ int layout_scene(gs_scene* s, const gs_scene_desc* d) {
 			uint32_t next_ref = start[h].refs;
 			for (int x = 0; x < 3; ++x) s->w_prim_base[3 * h + x] = next_prim[x];
 			const int* kids = wb.kids.data() + 8 * h;
+			if (h + 3 < nW)
+				for (int k = 0; k < 8; ++k) if (kids[24 + k] >= 0) __builtin_prefetch(N + kids[24 + k]);
 			for (int pass = 0; pass < 2; ++pass)
 				for (int k = 0; k < 8; ++k) {
 					const int c = kids[k];
@@ -566,7 +714,7 @@ int layout_scene(gs_scene* s, const gs_scene_desc* d) {
 						uint32_t dkind = kind;
 						if (kind == 0) {
 							sph_src[dev] = (int)idx;
-							if (d->spheres[idx].moving) { dkind = kKindMovingSphere; moving_seen = true; }
+							if (sflag[idx] & 1) { dkind = kKindMovingSphere; moving_seen = true; }
 						} else if (kind == 1) quad_src[dev] = (int)idx;
 						else tri_src[dev] = (int)idx;
 						last_ref = (dkind << kRefKindShift) | dev;
@@ -579,6 +727,7 @@ int layout_scene(gs_scene* s, const gs_scene_desc* d) {
 						s->h_leaf_code[c] = leaf_code((kind << 25) | idx, 0u);
 						if (kind != kKindMovingSphere) s->h_leaf_direct[c] = (int)idx;
 					}
+					if (s->h_leaf_direct[c] < 0) link_seen.store(true, std::memory_order_relaxed);
 				}
 		}, 4096);
 		any_moving = moving_seen.load();
@@ -602,7 +751,12 @@ int layout_scene(gs_scene* s, const gs_scene_desc* d) {
 				if (kids[k] >= 0 && N[kids[k]].ref_count == 0) stack.push_back(wb.child_base[h] + --r);
 		}
 	}
-	for (int i : sph_src) any_rot |= d->spheres[i].uv_rotation[0] != 1.0 || d->spheres[i].uv_rotation[1] != 0.0;
+	{
+		uint8_t all = 0;  // over every sphere of the description, placed or not: the table is only an optimisation
+		for (size_t i = 0; i < d->n_spheres; ++i) all |= sflag[i];
+		any_rot = (all & 2) != 0;
+	}
+	s->w_any_link = link_seen.load();
 	s->w_kids.swap(wb.kids);
 	s->w_child_base.swap(wb.child_base);
 	s->wide_depth = wb.depth;
@@ -669,6 +823,10 @@ int layout_scene(gs_scene* s, const gs_scene_desc* d) {
 		DSphere* sp = reinterpret_cast<DSphere*>(H + o_sph); double4* pa = reinterpret_cast<double4*>(H + o_sph_path);
 		int2* au = reinterpret_cast<int2*>(H + o_sph_aux); float2* ro = reinterpret_cast<float2*>(H + o_sph_rot);
 		parallel_for(nS, [&](size_t i) {
+			if (i + 8 < nS) {  // the device order is a walk of the tree, not the caller's order: start a later record's misses now
+				const char* nx = reinterpret_cast<const char*>(d->spheres + sph_src[i + 8]);
+				__builtin_prefetch(nx); __builtin_prefetch(nx + sizeof(gs_sphere) - 1);
+			}
 			const gs_sphere& g = d->spheres[sph_src[i]];
 			sp[i] = make_dsphere(g);
 			if (any_moving) pa[i] = make_double4(g.path[0], g.path[1], g.path[2], g.moving ? 1.0 : 0.0);
@@ -706,16 +864,16 @@ int layout_scene(gs_scene* s, const gs_scene_desc* d) {
 			md[i] = dm;
 		}
 		DMaterial* mats = reinterpret_cast<DMaterial*>(H + o_mat);
-		for (size_t i = 0; i < d->n_materials; ++i) {
+		parallel_for(d->n_materials, [&](size_t i) {
 			const gs_material& m = d->materials[i];
 			DMaterial dm;
 			dm.kind = m.kind; dm.tex = m.texture;
 			dm.ar = (float)m.albedo[0]; dm.ag = (float)m.albedo[1]; dm.ab = (float)m.albedo[2];
 			dm.param = (float)m.param; dm.pad0 = dm.pad1 = 0;
 			mats[i] = dm;
-		}
+		});
 		DTexture* texs = reinterpret_cast<DTexture*>(H + o_tex);
-		for (size_t i = 0; i < d->n_textures; ++i) {
+		parallel_for(d->n_textures, [&](size_t i) {
 			const gs_texture& t = d->textures[i];
 			DTexture dt;
 			dt.kind = t.kind; dt.a = t.a; dt.b = t.b; dt.scale = (float)t.scale;
@@ -723,7 +881,7 @@ int layout_scene(gs_scene* s, const gs_scene_desc* d) {
 			dt.scale_inv_d = t.kind == GS_TEX_CHECKER ? 1.0 / t.scale : 0.0;  // texture.rs:42,50
 			dt.scale_d = t.scale;
 			texs[i] = dt;
-		}
+		});
 		DImage* imgs = reinterpret_cast<DImage*>(H + o_img);
 		for (size_t i = 0; i < d->n_images; ++i) {
 			const gs_image& im = d->images[i];
@@ -772,6 +930,7 @@ int layout_scene(gs_scene* s, const gs_scene_desc* d) {
 	ds.perlin_perm = d->perlin_perm ? D + o_perm : nullptr;
 	ds.n_media = (int)d->n_media;
 	ds.root = root_leaf ? s->h_leaf_code[0] : 0;
+	ds.prmt_hi = 0x47000000u;
 	s->counters = reinterpret_cast<unsigned long long*>(D + o_counters);
 	s->stats = reinterpret_cast<unsigned long long*>(D + o_stats);
 	s->has_triangles = nT > 0;
@@ -871,13 +1030,7 @@ int build_nodes8(gs_scene* s, double origin_limit) {
 	if (s->wide_depth + 1 > kMaxStack8) return fail(GS_ERR_UNSUPPORTED, "eight-wide tree deeper than its traversal stack");
 	const double pad = pad_for(origin_limit, 12);
 	// does any leaf child need an explicit leaf code (several primitives, a moving sphere, a primitive placed elsewhere)?
-	std::atomic<bool> any_link{false};
-	parallel_for(nW, [&](size_t h) {
-		for (int k = 0; k < 8; ++k) {
-			const int c = s->w_kids[8 * h + k];
-			if (c >= 0 && N[c].ref_count > 0 && s->h_leaf_direct[c] < 0) { any_link = true; break; }
-		}
-	});
+	const bool any_link = s->w_any_link;
 	const size_t node_bytes = (nW * sizeof(DNode8) + 255) & ~(size_t)255;
 	const size_t link_bytes = any_link ? nW * 8 * sizeof(int) : 0;
 	Staging stg;
@@ -888,6 +1041,11 @@ int build_nodes8(gs_scene* s, double origin_limit) {
 	std::atomic<int> bad{0};
 	parallel_for(nW, [&](size_t h) {
 		const int* kids = s->w_kids.data() + 8 * h;
+		if (h + 3 < nW)  // the kids' records are scattered over the node array: start the misses of a later node now
+			for (int k = 0; k < 8; ++k) {
+				const int c = kids[24 + k];
+				if (c >= 0) { const char* p = reinterpret_cast<const char*>(N + c); __builtin_prefetch(p); __builtin_prefetch(p + sizeof(gs_bvh_node) - 1); }
+			}
 		float lo[8][3], hi[8][3];
 		float corner[3] = {INFINITY, INFINITY, INFINITY};
 		for (int k = 0; k < 8; ++k) {
@@ -912,7 +1070,12 @@ int build_nodes8(gs_scene* s, double origin_limit) {
 			for (int k = 0; k < 8; ++k) if (kids[k] >= 0) top = std::fmax(top, (double)hi[k][a]);
 			int e = -100;  // grid step 2^e: the smallest power of two whose 255 steps span the children (never below 2^-100)
 			const double extent0 = top - (double)corner[a];
-			if (extent0 > 0.0) e = std::max(e, (int)std::ceil(std::log2(extent0 / 250.0)));
+			if (extent0 > 0.0 && std::isfinite(extent0)) {  // ceil(log2(extent0 / 250)) from the exponent field; the loop below settles the rest
+				const double x = extent0 / 250.0;
+				int e0 = std::ilogb(x);
+				if (std::ldexp(1.0, e0) < x) ++e0;
+				e = std::max(e, e0);
+			}
 			float origin;
 			for (;; ++e) {
 				const double step = std::ldexp(1.0, e);
