@@ -162,6 +162,7 @@ int gs_scene_set_option(gs_scene* scene, const char* key, int64_t value) {
 		return GS_OK;
 	}
 	if (std::strcmp(key, "wavefront_sort") == 0) { scene->wavefront_sort = value != 0; return GS_OK; }
+	if (std::strcmp(key, "tail_ahead") == 0) { scene->tail_ahead = value != 0; return GS_OK; }
 	if (std::strcmp(key, "pool_capacity") == 0) {
 		if (value < 128 || value > (1ll << 26)) return fail(GS_ERR_INVALID, "pool_capacity out of range");
 		scene->pool_capacity = (int)value;
@@ -330,6 +331,7 @@ int gs_render_adaptive_accumulate(gs_scene* s, const gs_camera* camera, const gs
 	static const bool host_rounds = [] { const char* e = std::getenv("GS_ADAPTIVE_ROUNDS"); return !(e && std::strcmp(e, "kernel") == 0); }();
 	p.rounds_in_kernel = !host_rounds;
 	p.round0 = 0;
+	unsigned known_left = 0;  // the number of pixels handed to the tail kernel, when the host has read it
 	if (host_rounds) {
 		// one launch per batch + the stop test; after batches 1, 2, 4, 8 ... a 4-byte read tells whether to go on, to hand the
 		// last few pixels to the tail kernel, or to stop (synchronises the stream)
@@ -348,7 +350,11 @@ int gs_render_adaptive_accumulate(gs_scene* s, const gs_camera* camera, const gs
 				unsigned left = 0;
 				GS_CUDA(cudaMemcpyAsync(&left, s->px_count.p + nxt, sizeof left, cudaMemcpyDeviceToHost, st));
 				GS_CUDA(cudaStreamSynchronize(st));
-				if (left <= tail_pixels) break;
+				if (left <= tail_pixels) {
+					known_left = left;
+					if (std::getenv("GS_TRACE")) std::fprintf(stderr, "[gs_render_adaptive] %u pixels left after %llu batches: tail kernel\n", left, r + 1ull);
+					break;
+				}
 			}
 		}
 		GS_CUDA(cudaMemcpyAsync(s->px_count.p + 2, &which, sizeof which, cudaMemcpyHostToDevice, st));
@@ -365,7 +371,7 @@ int gs_render_adaptive_accumulate(gs_scene* s, const gs_camera* camera, const gs
 	tp.accum = static_cast<float4*>(d_accum); tp.lum = s->lum.p;
 	tp.work_counter = next_counter(s); tp.stats = s->stats;
 	GS_CUDA(cudaMemsetAsync(tp.work_counter, 0, sizeof(unsigned long long), st));
-	GS_CUDA(launch_adaptive_tail(tp, std::min(n_pixels, tail_pixels), s->sm_count, s->wide, st));
+	GS_CUDA(launch_adaptive_tail(tp, std::min(n_pixels, tail_pixels), s->tail_ahead ? known_left : 0u, s->sm_count, s->wide, st));
 	s->launches += 3;
 	return end_entry(s, st);
 }

@@ -154,6 +154,7 @@ struct gs_scene {
 	gs::DevBuf<int> shade_queue;        // material-sorted shading queues (kShadeClasses x pool slots)
 	gs::DevBuf<unsigned> shade_count;
 	bool wavefront_sort = false;        // option "wavefront_sort": measured 6...9 % slower than the unsorted queues (profiles/r02_v5_wavefront_sort.log)
+	bool tail_ahead = true;             // option "tail_ahead": adaptive tail renders several batches of a pixel at once when few pixels are left
 	gs::DevBuf<gs::WaveCounters> wave_ctr;
 	gs::WaveCounters* h_wave_ctr = nullptr;  // pinned
 

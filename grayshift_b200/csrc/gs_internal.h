@@ -47,7 +47,7 @@ struct AdaptiveTailParams {  // the last few pixels: one warp per pixel runs the
 // launch wrappers (defined next to the kernels); all asynchronous on `stream`
 cudaError_t launch_render_fixed(const RenderParams& p, int sm_count, bool count_nodes, bool triangles, cudaStream_t stream);
 cudaError_t launch_adaptive_init(uint32_t* list, unsigned* n_list, unsigned pixel_begin, unsigned pixel_stride, unsigned n_pixels, cudaStream_t stream);
-cudaError_t launch_adaptive_tail(const AdaptiveTailParams& p, unsigned n_upper, int sm_count, bool wide, cudaStream_t stream);
+cudaError_t launch_adaptive_tail(const AdaptiveTailParams& p, unsigned n_upper, unsigned n_known, int sm_count, bool wide, cudaStream_t stream);
 cudaError_t launch_adaptive_decide(const RenderParams& p, unsigned cur, cudaStream_t stream);  // host-driven rounds only
 cudaError_t launch_resolve(const float4* accum, int n_pixels, float* out_rgb, unsigned* out_counts, cudaStream_t stream);
 cudaError_t launch_resolve_rgb8(const float4* accum, int n_pixels, unsigned char* out_rgb8, unsigned* out_counts, cudaStream_t stream);

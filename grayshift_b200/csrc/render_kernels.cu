@@ -475,6 +475,92 @@ __global__ void __launch_bounds__(kBlock) adaptive_tail_kernel(const __grid_cons
 	flush_stats(P.stats, pc, paths);
 }
 
+// The same loop when only a few hundred pixels are left and the GPU is mostly idle: a pixel's batches are sequential by
+// definition and a batch lasts as long as its longest path (up to max_depth bounces), so a pixel that needs thirty more
+// batches holds the whole render for thirty path latencies (measured: 5.0 of scene 3's 7.0 ms, 1.2 of scene 1's 2.4).
+// Here a CTA of kWarps warps takes one pixel and renders its next kWarps batches AT ONCE -- batch b is the global sample
+// indices [b * batch_size, (b + 1) * batch_size) whoever renders it -- and then replays Camera::sample's loop over them in
+// order (camera.rs:137-164): the batches up to the one whose stop test fires are added, the rest are dropped, so the pixel
+// ends with exactly the samples the sequential loop gives it.  The dropped batches are work the reference would not have
+// done; they are not counted in the statistics (paths, rays, node visits are those of the batches kept).
+template <int kF, int kWarps>
+__global__ void __launch_bounds__(kWarps * 32) adaptive_tail_ahead_kernel(const __grid_constant__ AdaptiveTailParams P) {
+	__shared__ uint8_t s_perm[256];
+	__shared__ double s_part[kWarps][5];  // per batch: sum lum, sum lum^2, r, g, b
+	__shared__ unsigned long long s_k;
+	load_perm(s_perm, P.sc.perlin_perm);
+	const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+	const unsigned lt_mask = (1u << lane) - 1u;
+	const unsigned which = P.n_list[2] & 1u;
+	const unsigned n_list = P.n_list[which];
+	const uint32_t* const list = P.lists + (size_t)which * P.n_pixels;
+	PathCounters pc = {0u, 0u, 0u};
+	unsigned paths = 0;
+	for (;;) {
+		if (threadIdx.x == 0) s_k = atomicAdd(P.work_counter, 1ull);
+		__syncthreads();
+		const unsigned long long k = s_k;
+		__syncthreads();  // everybody has read s_k before it is written again
+		if (k >= n_list) break;
+		const uint32_t pixel = list[k];
+		const float4 a0 = P.accum[pixel];
+		const double2 l0 = P.lum[pixel];
+		double sample_count = (double)a0.w, tsum = l0.x, tsq = l0.y, tr = 0.0, tg = 0.0, tb = 0.0;  // the same on every thread
+		unsigned base = (unsigned)a0.w;  // global sample index of the pixel's next sample
+		for (;;) {
+			// this warp's batch
+			unsigned next = base + warp * P.batch_size;
+			const unsigned end = next + P.batch_size;
+			double sum = 0.0, sq_sum = 0.0, cr = 0.0, cg = 0.0, cb = 0.0;
+			PathCounters pcb = {0u, 0u, 0u};
+			unsigned started = 0;
+			PathState st;
+			bool alive = false;
+			for (;;) {
+				const unsigned dead = __ballot_sync(kFull, !alive);
+				if (dead) {
+					const unsigned avail = end - next;
+					if (!alive) {
+						const unsigned rank = __popc(dead & lt_mask);
+						if (rank < avail) { path_begin(st, P.cam, P.seed, pixel, next + rank); alive = true; ++started; }
+					}
+					const unsigned need = __popc(dead);
+					next += need < avail ? need : avail;
+				}
+				if (!__any_sync(kFull, alive)) break;
+				if (alive && path_step<kF>(P.sc, P.cam, s_perm, st, pcb)) {
+					cr += (double)st.L.x; cg += (double)st.L.y; cb += (double)st.L.z;
+					const double lum = 0.299 * (double)st.L.x + 0.587 * (double)st.L.y + 0.144 * (double)st.L.z;  // color.rs:31-33
+					sum += lum; sq_sum += lum * lum;
+					alive = false;
+				}
+			}
+			const double w0 = warp_sum(sum), w1 = warp_sum(sq_sum), w2 = warp_sum(cr), w3 = warp_sum(cg), w4 = warp_sum(cb);
+			if (lane == 0) { s_part[warp][0] = w0; s_part[warp][1] = w1; s_part[warp][2] = w2; s_part[warp][3] = w3; s_part[warp][4] = w4; }
+			__syncthreads();
+			bool stop = false;
+			unsigned kept = 0;
+			for (int w = 0; w < kWarps && !stop; ++w) {
+				sample_count += (double)P.batch_size;  // camera.rs:137
+				tsum += s_part[w][0]; tsq += s_part[w][1]; tr += s_part[w][2]; tg += s_part[w][3]; tb += s_part[w][4];
+				kept = (unsigned)w + 1u;
+				const double mean = tsum / sample_count;  // camera.rs:150-158
+				const double variance_sq = 1.0 / (sample_count - 1.0) * (tsq - tsum * tsum / sample_count);
+				const double convergence_sq = P.confidence_sq * variance_sq / sample_count;
+				if (convergence_sq < mean * mean * P.tolerance_sq) stop = true;
+				const unsigned sc_u32 = sample_count >= 4294967295.0 ? 4294967295u : (unsigned)sample_count;
+				if (sc_u32 > P.max_samples) stop = true;  // camera.rs:162-164
+			}
+			if (warp < kept) { pc.rays += pcb.rays; pc.tex_fetches += pcb.tex_fetches; pc.node_visits += pcb.node_visits; paths += started; }
+			base += (unsigned)kWarps * P.batch_size;
+			__syncthreads();  // s_part is rewritten by the next round
+			if (stop) break;
+		}
+		if (threadIdx.x == 0) P.accum[pixel] = make_float4(a0.x + (float)tr, a0.y + (float)tg, a0.z + (float)tb, (float)sample_count);
+	}
+	flush_stats(P.stats, pc, paths);
+}
+
 // pixel_color /= sample_count (camera.rs:167)
 __global__ void resolve_kernel(const float4* __restrict__ accum, int n_pixels, float* __restrict__ out_rgb, unsigned* __restrict__ out_counts) {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -609,7 +695,25 @@ cudaError_t launch_adaptive_init(uint32_t* list, unsigned* n_list, unsigned pixe
 	return cudaGetLastError();
 }
 
-cudaError_t launch_adaptive_tail(const AdaptiveTailParams& p, unsigned n_upper, int sm_count, bool wide, cudaStream_t stream) {
+// n_known: the length of the list if the host has read it (host-driven rounds), else 0.  Few pixels on an idle GPU:
+// several batches per pixel at once (adaptive_tail_ahead_kernel), as many as fit beside each other.
+cudaError_t launch_adaptive_tail(const AdaptiveTailParams& p, unsigned n_upper, unsigned n_known, int sm_count, bool wide, cudaStream_t stream) {
+	// tuning knobs: up to how many pixels a CTA of 4 / of 8 warps per pixel is used (0 = never)
+	static const unsigned ahead4 = [] { const char* e = std::getenv("GS_TAIL_AHEAD4"); return e ? (unsigned)std::atoi(e) : 2048u; }();
+	static const unsigned ahead8 = [] { const char* e = std::getenv("GS_TAIL_AHEAD8"); return e ? (unsigned)std::atoi(e) : 512u; }();
+	(void)sm_count;
+	if (n_known > 0 && (n_known <= ahead4 || n_known <= ahead8)) {
+		const bool eight = n_known <= ahead8;
+		const unsigned grid = n_known;
+		if (eight) {
+			if (wide) adaptive_tail_ahead_kernel<18, 8><<<grid, 256, 0, stream>>>(p);
+			else adaptive_tail_ahead_kernel<2, 8><<<grid, 256, 0, stream>>>(p);
+		} else {
+			if (wide) adaptive_tail_ahead_kernel<18, 4><<<grid, 128, 0, stream>>>(p);
+			else adaptive_tail_ahead_kernel<2, 4><<<grid, 128, 0, stream>>>(p);
+		}
+		return cudaGetLastError();
+	}
 	int per_sm = 0;
 	if (wide) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, adaptive_tail_kernel<18>, kBlock, 0);
 	else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, adaptive_tail_kernel<2>, kBlock, 0);

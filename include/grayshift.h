@@ -275,6 +275,8 @@ int gs_render_adaptive_accumulate(gs_scene* scene, const gs_camera* camera, cons
 /* Options: "count_nodes" (0/1) switches to the kernel variant that counts BVH node fetches and texel reads;
  * "wavefront" (0/1) selects the wavefront pipeline for fixed-count renders; "pool_capacity" its path pool size;
  * "wavefront_sort" (0/1, default 0) its material-sorted shading queues;
+ * "tail_ahead" (0/1, default 1): when the adaptive sampler is down to a few hundred pixels, render several of a pixel's
+ * batches at once and keep those up to the one whose stop test fires (same samples and counts as the sequential loop);
  * "bvh_width" (2 or 8) selects the tree the kernels traverse -- the binary tree or the eight-wide compressed tree
  * the library derives from it (default: by scene size; the other tree is built on first request). */
 int gs_scene_set_option(gs_scene* scene, const char* key, int64_t value);

@@ -310,3 +310,21 @@ def test_render_multi_splits_over_every_gpu_of_the_box(name, kw):
         assert sa.paths == sb.paths and abs(int(sa.rays) - int(sb.rays)) <= 1e-4 * int(sa.rays)
         assert np.allclose(a, b, rtol=2e-4, atol=1e-5), f"{g} GPUs: image differs"
         assert sb.exchange_ms > 0.0
+
+
+@pytest.mark.parametrize("name,kw,width", [("scene6", {"width": 96}, 2), ("scene3", {"width": 160}, 2), ("scene1", {"width": 200}, 2),
+                                           ("scene1", {"width": 200}, 8), ("scene11", {"width": 120}, 2)])
+def test_adaptive_tail_rendering_batches_ahead_keeps_the_sequential_result(name, kw, width):
+    """Few pixels left: the tail kernel renders several of a pixel's batches at once and replays Camera::sample's loop over them
+    in order (camera.rs:137-164).  Batch b is the same global sample indices whoever renders it, so counts are identical to the
+    one-batch-at-a-time tail and the image differs only by the order of float additions; dropped batches do not show in the stats."""
+    host = gs.HostScene.build(name, **kw)
+    dev = gs.DeviceScene(host)
+    dev.set_option("bvh_width", width)
+    dev.set_option("tail_ahead", 0)
+    a, ca, sa = dev.render(seed=9)
+    dev.set_option("tail_ahead", 1)
+    b, cb, sb = dev.render(seed=9)
+    assert np.array_equal(ca, cb)
+    assert sa.paths == sb.paths == ca.sum() and sa.rays == sb.rays
+    assert np.allclose(a, b, rtol=1e-4, atol=1e-6)
