@@ -332,6 +332,7 @@ int gs_render_adaptive_accumulate(gs_scene* s, const gs_camera* camera, const gs
 	p.rounds_in_kernel = !host_rounds;
 	p.round0 = 0;
 	unsigned known_left = 0;  // the number of pixels handed to the tail kernel, when the host has read it
+	bool need_tail = !host_rounds;
 	if (host_rounds) {
 		// one launch per batch + the stop test; after batches 1, 2, 4, 8 ... a 4-byte read tells whether to go on, to hand the
 		// last few pixels to the tail kernel, or to stop (synchronises the stream)
@@ -350,19 +351,23 @@ int gs_render_adaptive_accumulate(gs_scene* s, const gs_camera* camera, const gs
 				unsigned left = 0;
 				GS_CUDA(cudaMemcpyAsync(&left, s->px_count.p + nxt, sizeof left, cudaMemcpyDeviceToHost, st));
 				GS_CUDA(cudaStreamSynchronize(st));
+				static const bool trace = std::getenv("GS_TRACE") != nullptr;
+				if (trace) std::fprintf(stderr, "[gs_render_adaptive] %u of %u pixels left after %llu batches%s\n", left, n_pixels, r + 1ull, left <= tail_pixels ? ": tail kernel" : "");
 				if (left <= tail_pixels) {
 					known_left = left;
-					if (std::getenv("GS_TRACE")) std::fprintf(stderr, "[gs_render_adaptive] %u pixels left after %llu batches: tail kernel\n", left, r + 1ull);
+					need_tail = left > 0;
 					break;
 				}
 			}
 		}
-		GS_CUDA(cudaMemcpyAsync(s->px_count.p + 2, &which, sizeof which, cudaMemcpyHostToDevice, st));
-		GS_CUDA(cudaStreamSynchronize(st));  // `which` is a stack variable
+		// (a loop that ran all its rounds has stopped every pixel: max_samples, camera.rs:162-164)
+		// which list the tail kernel reads: it looks at bit 0 only, so a byte fill will do -- no host buffer to keep alive
+		if (need_tail) GS_CUDA(cudaMemsetAsync(s->px_count.p + 2, (int)which, sizeof(unsigned), st));
 	} else
 	// (alternative) every batch round in one cooperative launch (render, grid sync, stop test, grid sync ...) until at most
 	// tail_pixels pixels are left; then one warp per remaining pixel finishes its loop.  No host round trip.
 	GS_CUDA(launch_render_fixed(p, s->sm_count, false, s->has_triangles, st));
+	if (!need_tail) { s->launches += 1; return end_entry(s, st); }  // (the list initialisation)
 	AdaptiveTailParams tp;
 	tp.sc = s->ds; tp.cam = p.cam; tp.seed = seed;
 	tp.confidence_sq = confidence_sq; tp.tolerance_sq = tolerance_sq;

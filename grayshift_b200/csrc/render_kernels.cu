@@ -698,8 +698,10 @@ cudaError_t launch_adaptive_init(uint32_t* list, unsigned* n_list, unsigned pixe
 // n_known: the length of the list if the host has read it (host-driven rounds), else 0.  Few pixels on an idle GPU:
 // several batches per pixel at once (adaptive_tail_ahead_kernel), as many as fit beside each other.
 cudaError_t launch_adaptive_tail(const AdaptiveTailParams& p, unsigned n_upper, unsigned n_known, int sm_count, bool wide, cudaStream_t stream) {
-	// tuning knobs: up to how many pixels a CTA of 4 / of 8 warps per pixel is used (0 = never)
-	static const unsigned ahead4 = [] { const char* e = std::getenv("GS_TAIL_AHEAD4"); return e ? (unsigned)std::atoi(e) : 2048u; }();
+	// tuning knobs: up to how many pixels a CTA of 4 / of 8 warps per pixel is used (0 = never).  Measured on the reference's
+	// scenes 1 and 3 (2450 pixels left after the first batch; profiles/r02_v8_adaptive_tail_ahead.log): one warp per pixel 2.39 /
+	// 7.02 ms for the whole render, four 1.83 / 3.66, eight 2.29 / 3.73.
+	static const unsigned ahead4 = [] { const char* e = std::getenv("GS_TAIL_AHEAD4"); return e ? (unsigned)std::atoi(e) : 8192u; }();
 	static const unsigned ahead8 = [] { const char* e = std::getenv("GS_TAIL_AHEAD8"); return e ? (unsigned)std::atoi(e) : 512u; }();
 	(void)sm_count;
 	if (n_known > 0 && (n_known <= ahead4 || n_known <= ahead8)) {

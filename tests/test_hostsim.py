@@ -258,3 +258,29 @@ def test_a_primitive_referenced_by_two_leaves(width):
             ok = ok & ~take & (best != k)
     assert np.array_equal(ids, np.where(best >= 0, 100 + best, -1))
     L.hs_scene_destroy(h)
+
+
+def test_layout_loops_survive_fork_and_concurrent_callers():
+    """The layout's loops run on a process-wide worker pool.  A forked child has the pool object but none of its threads, and a
+    second host thread may start a loop while the pool is busy: both must fall back to running the loop themselves."""
+    import threading
+
+    host = gs.HostScene.build("c5", width=64, spp=1, n_spheres=60000)
+    ref = SimScene(host, 8).info()
+    import warnings
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", DeprecationWarning)  # forking a multi-threaded process is the point of the test
+        pid = os.fork()
+    if pid == 0:
+        ok = SimScene(host, 8).info() == ref
+        os._exit(0 if ok else 1)
+    _, status = os.waitpid(pid, 0)
+    assert status == 0
+    out = []
+    ts = [threading.Thread(target=lambda: out.append(SimScene(host, 8).info())) for _ in range(4)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert out == [ref] * 4
