@@ -163,6 +163,11 @@ int gs_scene_set_option(gs_scene* scene, const char* key, int64_t value) {
 	}
 	if (std::strcmp(key, "wavefront_sort") == 0) { scene->wavefront_sort = value != 0; return GS_OK; }
 	if (std::strcmp(key, "tail_ahead") == 0) { scene->tail_ahead = value != 0; return GS_OK; }
+	if (std::strcmp(key, "adaptive_chains") == 0) {
+		if (value < 0 || value > kMaxChains) return fail(GS_ERR_INVALID, "adaptive_chains: 0 (by image size) to 4");
+		scene->adaptive_chains = (int)value;
+		return GS_OK;
+	}
 	if (std::strcmp(key, "pool_capacity") == 0) {
 		if (value < 128 || value > (1ll << 26)) return fail(GS_ERR_INVALID, "pool_capacity out of range");
 		scene->pool_capacity = (int)value;
@@ -298,86 +303,141 @@ int gs_render_adaptive_accumulate(gs_scene* s, const gs_camera* camera, const gs
 	if (rounds * settings->batch_size > (1ull << 24)) return fail(GS_ERR_UNSUPPORTED, "adaptive sampling beyond 2^24 samples per pixel");
 	rc = begin_entry(s, st);
 	if (rc) return rc;
-	GS_CUDA(s->px_list[0].alloc((size_t)n_pixels * 2, st));  // the two lists of the rounds, back to back
-	GS_CUDA(s->px_count.alloc(4, st));
-	GS_CUDA(s->lum.alloc(total, st));
-	GS_CUDA(cudaMemsetAsync(s->lum.p, 0, (size_t)total * sizeof(double2), st));
-	GS_CUDA(launch_adaptive_init(s->px_list[0].p, s->px_count.p, pixel_begin, pixel_stride, n_pixels, st));
-	p.seed = seed;
-	p.sample_begin = 0;
-	p.sample_count = settings->batch_size;
-	p.total_items = (unsigned long long)n_pixels * settings->batch_size;  // upper bound (sizes the grid); the kernel reads the list lengths
-	p.chunk = 256;
-	p.accum = static_cast<float4*>(d_accum);
-	p.stats = s->stats;
-	p.lum = s->lum.p;
-	p.small_scene = s->small_scene;
-	p.wide = s->wide;
-	p.pixel_list = s->px_list[0].p;
-	p.n_list = s->px_count.p;
-	p.work_counter = next_counter(s);
-	p.work_counter2 = next_counter(s);
-	p.confidence_sq = confidence_sq; p.tolerance_sq = tolerance_sq;
-	p.max_samples = settings->max_samples; p.n_pixels = n_pixels;
 	static const unsigned tail_pixels = [] { const char* e = std::getenv("GS_TAIL_PIXELS"); return e ? (unsigned)std::atoi(e) : kAdaptiveTailPixels; }();  // tuning knob
-	p.tail_pixels = tail_pixels;
-	GS_CUDA(cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned long long), st));
-	GS_CUDA(cudaMemsetAsync(p.work_counter2, 0, sizeof(unsigned long long), st));
 	// Who drives the batch rounds.  Default: the host (one render launch + the stop test per batch, a 4-byte "anyone left?" read after
 	// batches 1, 2, 4, 8 ...).  GS_ADAPTIVE_ROUNDS=kernel: all rounds inside one cooperative launch with grid-wide syncs in between --
 	// no host round trip, but measured 2...15 % slower on every scene of main.rs (profiles/r02_v4_adaptive_rounds_host_vs_kernel.log:
 	// the final scene at 400x400 141 vs 165 ms): CTAs that finish a round early spin at the grid barrier next to the ones still
 	// rendering and every arrival invalidates the SM's L1, where a kernel boundary simply frees the SM.
 	static const bool host_rounds = [] { const char* e = std::getenv("GS_ADAPTIVE_ROUNDS"); return !(e && std::strcmp(e, "kernel") == 0); }();
+	// Chains.  A round's launch ends with a drain: the queue is empty, the SMs go idle one by one, and the launch lasts until its
+	// longest path is done (the final scene at 400x400: 5 M paths per round, the SMs busy 79 % of the launch,
+	// profiles/r02_v10_scene8_adaptive_round_raw.csv).  The stop test is per pixel, so the pixels are dealt out to a few independent
+	// chains of rounds, each on its own stream: while one chain's launch drains, the next chain's launch takes over the idle SMs.
+	static const unsigned max_chains = [] { const char* e = std::getenv("GS_ADAPTIVE_CHAINS"); const int v = e ? std::atoi(e) : 2; return (unsigned)(v < 1 ? 1 : (v > kMaxChains ? kMaxChains : v)); }();
+	// (measured, profiles/r02_v11_adaptive_chains.log, 1 / 2 / 3 / 4 chains: the final scene at 400x400 142 / 123 / 125 / 129 ms, at 800x800
+	// 397 / 366 / 377 / 389, scene 5 94 / 76 / 77 / 77, Cornell 90 / 87 / 91 / 94; renders of 90 k pixels lose 0.2 ms to the extra launches,
+	// hence the 65536 pixels a chain must have)
+	unsigned K = host_rounds ? std::min(max_chains, std::max(1u, n_pixels / 65536u)) : 1u;
+	if (host_rounds && s->adaptive_chains > 0) K = std::min((unsigned)s->adaptive_chains, std::max(1u, n_pixels / 64u));  // option "adaptive_chains"
+	if (K > 1 && !s->aux_ready) {
+		for (int c = 0; c < kMaxChains - 1; ++c) {
+			GS_CUDA(cudaStreamCreateWithFlags(&s->aux[c], cudaStreamNonBlocking));
+			GS_CUDA(cudaEventCreateWithFlags(&s->aux_done[c], cudaEventDisableTiming));
+		}
+		GS_CUDA(cudaEventCreateWithFlags(&s->aux_begin, cudaEventDisableTiming));
+		s->aux_ready = true;
+	}
+	GS_CUDA(s->px_list[0].alloc((size_t)n_pixels * 2, st));  // per chain the two lists of its rounds, back to back
+	GS_CUDA(s->px_count.alloc(4 * kMaxChains, st));
+	GS_CUDA(s->lum.alloc(total, st));
+	GS_CUDA(cudaMemsetAsync(s->lum.p, 0, (size_t)total * sizeof(double2), st));
+	p.seed = seed;
+	p.sample_begin = 0;
+	p.sample_count = settings->batch_size;
+	p.chunk = 256;
+	p.accum = static_cast<float4*>(d_accum);
+	p.stats = s->stats;
+	p.lum = s->lum.p;
+	p.small_scene = s->small_scene;
+	p.wide = s->wide;
+	p.confidence_sq = confidence_sq; p.tolerance_sq = tolerance_sq;
+	p.max_samples = settings->max_samples;
+	p.tail_pixels = tail_pixels;
 	p.rounds_in_kernel = !host_rounds;
 	p.round0 = 0;
-	unsigned known_left = 0;  // the number of pixels handed to the tail kernel, when the host has read it
-	bool need_tail = !host_rounds;
+	struct Chain {
+		cudaStream_t st = nullptr;
+		RenderParams p;
+		unsigned n = 0;           // pixels of this chain
+		unsigned which = 0;       // the list holding the pixels still sampling
+		unsigned left = 0;        // host copy of its length (valid after a check)
+		unsigned known_left = 0;  // the number of pixels handed to the tail kernel, when the host has read it
+		bool active = true, need_tail = false;
+	} chain[kMaxChains];
+	size_t list_at = 0;
+	for (unsigned c = 0; c < K; ++c) {
+		Chain& ch = chain[c];
+		ch.st = c == 0 ? st : s->aux[c - 1];
+		ch.n = (n_pixels - c + K - 1) / K;  // list entries c, c + K, c + 2K ... of the whole render
+		ch.p = p;
+		ch.p.n_pixels = ch.n;
+		ch.p.total_items = (unsigned long long)ch.n * settings->batch_size;  // upper bound (sizes the grid); the kernel reads the list lengths
+		ch.p.pixel_list = s->px_list[0].p + list_at;
+		ch.p.n_list = s->px_count.p + 4 * c;
+		ch.p.work_counter = next_counter(s);
+		ch.p.work_counter2 = next_counter(s);
+		ch.need_tail = !host_rounds;
+		list_at += (size_t)ch.n * 2;
+		GS_CUDA(launch_adaptive_init(ch.p.pixel_list, ch.p.n_list, pixel_begin + c * pixel_stride, pixel_stride * K, ch.n, st));
+		GS_CUDA(cudaMemsetAsync(ch.p.work_counter, 0, sizeof(unsigned long long), st));
+		GS_CUDA(cudaMemsetAsync(ch.p.work_counter2, 0, sizeof(unsigned long long), st));
+		s->launches += 1;
+	}
+	if (K > 1) {
+		GS_CUDA(cudaEventRecord(s->aux_begin, st));
+		for (unsigned c = 1; c < K; ++c) GS_CUDA(cudaStreamWaitEvent(chain[c].st, s->aux_begin, 0));
+	}
+	static const bool trace = std::getenv("GS_TRACE") != nullptr;
 	if (host_rounds) {
-		// one launch per batch + the stop test; after batches 1, 2, 4, 8 ... a 4-byte read tells whether to go on, to hand the
-		// last few pixels to the tail kernel, or to stop (synchronises the stream)
-		unsigned which = 0;
+		// one launch per batch and chain + the stop test; after batches 1, 2, 4, 8 ... a 4-byte read per chain tells whether to go on,
+		// to hand the last few pixels to the tail kernel, or to stop (synchronises the streams)
 		for (unsigned long long r = 0; r < rounds; ++r) {
 			const unsigned cur = (unsigned)(r & 1ull), nxt = cur ^ 1u;
-			p.round0 = (unsigned)r;
-			p.work_counter = next_counter(s);
-			GS_CUDA(cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned long long), st));
-			GS_CUDA(cudaMemsetAsync(s->px_count.p + nxt, 0, sizeof(unsigned), st));
-			GS_CUDA(launch_render_fixed(p, s->sm_count, false, s->has_triangles, st));
-			GS_CUDA(launch_adaptive_decide(p, cur, st));
-			s->launches += 2;
-			which = nxt;
+			bool any = false;
+			for (unsigned c = 0; c < K; ++c) {
+				Chain& ch = chain[c];
+				if (!ch.active) continue;
+				any = true;
+				ch.p.round0 = (unsigned)r;
+				ch.p.work_counter = next_counter(s);
+				GS_CUDA(cudaMemsetAsync(ch.p.work_counter, 0, sizeof(unsigned long long), ch.st));
+				GS_CUDA(cudaMemsetAsync(ch.p.n_list + nxt, 0, sizeof(unsigned), ch.st));
+				GS_CUDA(launch_render_fixed(ch.p, s->sm_count, false, s->has_triangles, ch.st));
+				GS_CUDA(launch_adaptive_decide(ch.p, cur, ch.st));
+				s->launches += 2;
+				ch.which = nxt;
+			}
+			if (!any) break;
 			if (((r + 1ull) & r) == 0ull && r + 1 < rounds) {
-				unsigned left = 0;
-				GS_CUDA(cudaMemcpyAsync(&left, s->px_count.p + nxt, sizeof left, cudaMemcpyDeviceToHost, st));
-				GS_CUDA(cudaStreamSynchronize(st));
-				static const bool trace = std::getenv("GS_TRACE") != nullptr;
-				if (trace) std::fprintf(stderr, "[gs_render_adaptive] %u of %u pixels left after %llu batches%s\n", left, n_pixels, r + 1ull, left <= tail_pixels ? ": tail kernel" : "");
-				if (left <= tail_pixels) {
-					known_left = left;
-					need_tail = left > 0;
-					break;
+				for (unsigned c = 0; c < K; ++c)
+					if (chain[c].active) GS_CUDA(cudaMemcpyAsync(&chain[c].left, chain[c].p.n_list + nxt, sizeof(unsigned), cudaMemcpyDeviceToHost, chain[c].st));
+				for (unsigned c = 0; c < K; ++c) {
+					Chain& ch = chain[c];
+					if (!ch.active) continue;
+					GS_CUDA(cudaStreamSynchronize(ch.st));
+					const unsigned share = tail_pixels / K;
+					if (trace) std::fprintf(stderr, "[gs_render_adaptive] chain %u: %u of %u pixels left after %llu batches%s\n", c, ch.left, ch.n, r + 1ull, ch.left <= share ? ": tail kernel" : "");
+					if (ch.left <= share) { ch.known_left = ch.left; ch.need_tail = ch.left > 0; ch.active = false; }
 				}
 			}
 		}
-		// (a loop that ran all its rounds has stopped every pixel: max_samples, camera.rs:162-164)
-		// which list the tail kernel reads: it looks at bit 0 only, so a byte fill will do -- no host buffer to keep alive
-		if (need_tail) GS_CUDA(cudaMemsetAsync(s->px_count.p + 2, (int)which, sizeof(unsigned), st));
+		// (a chain that ran all its rounds has stopped every pixel: max_samples, camera.rs:162-164)
 	} else
 	// (alternative) every batch round in one cooperative launch (render, grid sync, stop test, grid sync ...) until at most
 	// tail_pixels pixels are left; then one warp per remaining pixel finishes its loop.  No host round trip.
-	GS_CUDA(launch_render_fixed(p, s->sm_count, false, s->has_triangles, st));
-	if (!need_tail) { s->launches += 1; return end_entry(s, st); }  // (the list initialisation)
-	AdaptiveTailParams tp;
-	tp.sc = s->ds; tp.cam = p.cam; tp.seed = seed;
-	tp.confidence_sq = confidence_sq; tp.tolerance_sq = tolerance_sq;
-	tp.batch_size = settings->batch_size; tp.max_samples = settings->max_samples;
-	tp.lists = s->px_list[0].p; tp.n_list = s->px_count.p; tp.n_pixels = n_pixels;
-	tp.accum = static_cast<float4*>(d_accum); tp.lum = s->lum.p;
-	tp.work_counter = next_counter(s); tp.stats = s->stats;
-	GS_CUDA(cudaMemsetAsync(tp.work_counter, 0, sizeof(unsigned long long), st));
-	GS_CUDA(launch_adaptive_tail(tp, std::min(n_pixels, tail_pixels), s->tail_ahead ? known_left : 0u, s->sm_count, s->wide, st));
-	s->launches += 3;
+	{ GS_CUDA(launch_render_fixed(chain[0].p, s->sm_count, false, s->has_triangles, st)); s->launches += 1; }
+	for (unsigned c = 0; c < K; ++c) {
+		Chain& ch = chain[c];
+		if (ch.need_tail) {
+			// which list the tail kernel reads: it looks at bit 0 only, so a byte fill will do -- no host buffer to keep alive
+			if (host_rounds) GS_CUDA(cudaMemsetAsync(ch.p.n_list + 2, (int)ch.which, sizeof(unsigned), ch.st));
+			AdaptiveTailParams tp;
+			tp.sc = s->ds; tp.cam = p.cam; tp.seed = seed;
+			tp.confidence_sq = confidence_sq; tp.tolerance_sq = tolerance_sq;
+			tp.batch_size = settings->batch_size; tp.max_samples = settings->max_samples;
+			tp.lists = ch.p.pixel_list; tp.n_list = ch.p.n_list; tp.n_pixels = ch.n;
+			tp.accum = static_cast<float4*>(d_accum); tp.lum = s->lum.p;
+			tp.work_counter = next_counter(s); tp.stats = s->stats;
+			GS_CUDA(cudaMemsetAsync(tp.work_counter, 0, sizeof(unsigned long long), ch.st));
+			GS_CUDA(launch_adaptive_tail(tp, std::min(ch.n, tail_pixels), s->tail_ahead ? ch.known_left : 0u, s->sm_count, s->wide, ch.st));
+			s->launches += 1;
+		}
+		if (c > 0) {  // the caller's stream continues after every chain
+			GS_CUDA(cudaEventRecord(s->aux_done[c - 1], ch.st));
+			GS_CUDA(cudaStreamWaitEvent(st, s->aux_done[c - 1], 0));
+		}
+	}
 	return end_entry(s, st);
 }
 

@@ -73,7 +73,8 @@ void staging_release(Staging& s, cudaEvent_t busy_until);  // the block is reuse
 void staging_forget_event(cudaEvent_t ev);                  // an event that is about to be destroyed no longer guards a block
 const char* last_error_cstr();
 
-constexpr int kCounterSlots = 64;
+constexpr int kCounterSlots = 256;
+constexpr int kMaxChains = 4;      // independent chains of adaptive rounds (gs_render_adaptive_accumulate)
 constexpr size_t kSmallSceneBytes = 128u << 10;  // C1 (486 spheres) is 47 KB, C3 2 KB, C4 (the one that wants the spill-free build) 490 KB
 constexpr unsigned kAdaptiveTailPixels = 8192;   // adaptive renders: below this many unfinished pixels, switch to one warp per pixel (measured 256 / 2048 / 8192: profiles/r02_v2_adaptive_times.log)
 constexpr int kStatSlots = 16;                   // [0..3] = gs_stats totals; [4..] only written by the GS_DIVERGENCE_STATS diagnostic build
@@ -121,6 +122,9 @@ struct gs_scene {
 	bool wide = false;           // which tree the kernels traverse
 
 	// adaptive sampler: the two lists of pixels still sampling, their lengths, per-pixel (sum lum, sum lum^2)
+	cudaStream_t aux[gs::kMaxChains - 1] = {};        // streams of the adaptive sampler's extra chains, made on first use
+	cudaEvent_t aux_done[gs::kMaxChains - 1] = {}, aux_begin = nullptr;
+	bool aux_ready = false;
 	gs::DevBuf<uint32_t> px_list[2];
 	gs::DevBuf<unsigned> px_count;
 	gs::DevBuf<double2> lum;
@@ -154,6 +158,7 @@ struct gs_scene {
 	gs::DevBuf<int> shade_queue;        // material-sorted shading queues (kShadeClasses x pool slots)
 	gs::DevBuf<unsigned> shade_count;
 	bool wavefront_sort = false;        // option "wavefront_sort": measured 6...9 % slower than the unsorted queues (profiles/r02_v5_wavefront_sort.log)
+	int adaptive_chains = 0;            // option "adaptive_chains": independent chains of adaptive rounds, 0 = chosen by the image size
 	bool tail_ahead = true;             // option "tail_ahead": adaptive tail renders several batches of a pixel at once when few pixels are left
 	gs::DevBuf<gs::WaveCounters> wave_ctr;
 	gs::WaveCounters* h_wave_ctr = nullptr;  // pinned

@@ -1182,5 +1182,7 @@ gs_scene::~gs_scene() {
 	if (last) cudaEventDestroy(last);
 	if (ev0) cudaEventDestroy(ev0);
 	if (ev1) cudaEventDestroy(ev1);
+	for (int c = 0; c < gs::kMaxChains - 1; ++c) { if (aux_done[c]) cudaEventDestroy(aux_done[c]); if (aux[c]) cudaStreamDestroy(aux[c]); }
+	if (aux_begin) cudaEventDestroy(aux_begin);
 	if (up) { cudaStreamSynchronize(up); cudaStreamDestroy(up); }
 }

@@ -277,6 +277,8 @@ int gs_render_adaptive_accumulate(gs_scene* scene, const gs_camera* camera, cons
  * "wavefront_sort" (0/1, default 0) its material-sorted shading queues;
  * "tail_ahead" (0/1, default 1): when the adaptive sampler is down to a few hundred pixels, render several of a pixel's
  * batches at once and keep those up to the one whose stop test fires (same samples and counts as the sequential loop);
+ * "adaptive_chains" (0..4, default 0 = by image size: 2 from 131072 pixels): the adaptive sampler deals the pixels out to this many
+ * independent chains of rounds on streams of their own, so that one chain's launch fills the SMs another's leaves idle as it ends;
  * "bvh_width" (2 or 8) selects the tree the kernels traverse -- the binary tree or the eight-wide compressed tree
  * the library derives from it (default: by scene size; the other tree is built on first request). */
 int gs_scene_set_option(gs_scene* scene, const char* key, int64_t value);

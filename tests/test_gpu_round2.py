@@ -328,3 +328,21 @@ def test_adaptive_tail_rendering_batches_ahead_keeps_the_sequential_result(name,
     assert np.array_equal(ca, cb)
     assert sa.paths == sb.paths == ca.sum() and sa.rays == sb.rays
     assert np.allclose(a, b, rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("name,kw", [("scene6", {"width": 96}), ("scene8", {"width": 120}), ("scene1", {"width": 200})])
+def test_adaptive_chains_render_the_same_image(name, kw):
+    """The stop test is per pixel (camera.rs:125-171), so the pixels can be dealt out to independent chains of rounds on streams of
+    their own (the launches of one chain fill the SMs another leaves idle as it ends).  Same samples per pixel whatever the
+    number of chains: identical counts and statistics, radiance up to the order of float additions."""
+    host = gs.HostScene.build(name, **kw)
+    dev = gs.DeviceScene(host)
+    dev.set_option("adaptive_chains", 1)
+    a, ca, sa = dev.render(seed=5)
+    for k in (2, 3, 4):
+        dev.set_option("adaptive_chains", k)
+        b, cb, sb = dev.render(seed=5)
+        assert np.array_equal(ca, cb), k
+        assert sa.paths == sb.paths and sa.rays == sb.rays
+        assert np.allclose(a, b, rtol=1e-4, atol=1e-6)
+        assert sb.kernel_launches > sa.kernel_launches
