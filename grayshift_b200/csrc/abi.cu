@@ -92,6 +92,17 @@ template <class T> struct Scratch {
 	~Scratch() { b.release(st); }
 };
 
+// Work items a warp takes from the queue at a time.  A launch ends when the last chunk taken is done, and a warp needs about
+// 2 us per path while the SMs are full.  Fixed-count launches: 256 (64 costs the 500-spp step 3.5 %: a division, an atomic and
+// a pixel flush more often; even at 16 spp per launch 256 is not worse).  Rounds of the adaptive sampler, a few million paths of
+// 32 per pixel each: 128 (256 / 128 / 64 / 32 with two chains: final scene 400x400 125.7 / 116.3 / 115.3 / 117.3 ms, 800x800
+// 363.9 / 364.0 / 369.4 / 380.4, scene 1 1.79 / 1.60 / 1.57 / 1.54; profiles/r02_v12_adaptive_chunk.log).
+unsigned chunk_items(bool adaptive_round) {
+	static const int forced = [] { const char* e = std::getenv("GS_CHUNK"); return e ? std::atoi(e) : 0; }();  // tuning knob
+	if (forced >= 32) return (unsigned)forced;
+	return adaptive_round ? 128u : 256u;
+}
+
 unsigned long long* next_counter(gs_scene* s) {
 	unsigned long long* p = s->counters + s->next_counter;
 	s->next_counter = (s->next_counter + 1) % kCounterSlots;
@@ -243,7 +254,7 @@ int gs_issue_fixed(gs_scene* s, const DCamera& cam, uint64_t seed, uint32_t samp
 		w.total_items = p.total_items; w.accum = static_cast<float4*>(d_accum); w.stats = s->stats;
 		return render_wavefront(s, w, st);
 	}
-	p.chunk = 256;
+	p.chunk = chunk_items(false);
 	p.accum = static_cast<float4*>(d_accum);
 	p.work_counter = next_counter(s);
 	p.stats = s->stats;
@@ -335,7 +346,7 @@ int gs_render_adaptive_accumulate(gs_scene* s, const gs_camera* camera, const gs
 	p.seed = seed;
 	p.sample_begin = 0;
 	p.sample_count = settings->batch_size;
-	p.chunk = 256;
+	p.chunk = 256;  // (set per chain below)
 	p.accum = static_cast<float4*>(d_accum);
 	p.stats = s->stats;
 	p.lum = s->lum.p;
@@ -363,6 +374,7 @@ int gs_render_adaptive_accumulate(gs_scene* s, const gs_camera* camera, const gs
 		ch.p = p;
 		ch.p.n_pixels = ch.n;
 		ch.p.total_items = (unsigned long long)ch.n * settings->batch_size;  // upper bound (sizes the grid); the kernel reads the list lengths
+		ch.p.chunk = chunk_items(true);
 		ch.p.pixel_list = s->px_list[0].p + list_at;
 		ch.p.n_list = s->px_count.p + 4 * c;
 		ch.p.work_counter = next_counter(s);
