@@ -168,6 +168,34 @@ struct PathRng {
 		++draw;
 		return w == 0 ? buf.x : (w == 1 ? buf.y : (w == 2 ? buf.z : buf.w));
 	}
+	// The next K (<= 4) draws at once -- the same words next_u32() would return one by one.  With single draws every call
+	// site carries its own copy of the ten Philox rounds and runs it for the quarter of the lanes whose draw counter sits
+	// on a block boundary there (measured 2.8 active lanes on config 5, 7 % of the kernel's instructions); taking the draws
+	// of a bounce together needs at most one block, computed once for all lanes that need one.
+	// The words come from old[w..3] followed by the new block; with w == 0 nothing of the old block is left.
+#ifndef GS_RNG_TAKE
+#define GS_RNG_TAKE 1  // tuning knob: 0 = K single draws
+#endif
+	template <int K>
+	__device__ __forceinline__ void take(uint32_t (&out)[K]) {
+		static_assert(K >= 1 && K <= 3, "take: one to three draws");
+#if GS_RNG_TAKE
+		const uint32_t w = draw & 3u;
+		const uint4 o = buf;
+		if (w == 0u || w + (uint32_t)K > 4u) buf = philox4x32_10(pixel, sample, (draw + 3u) >> 2, 0u, k0, k1);  // the block after `o`, or of draw itself when w == 0
+		const uint4 n = buf;
+		const bool w0 = w == 0u, w1 = w == 1u, w2 = w == 2u;
+		out[0] = w0 ? n.x : (w1 ? o.y : (w2 ? o.z : o.w));
+		if (K > 1) out[1] = w0 ? n.y : (w1 ? o.z : (w2 ? o.w : n.x));
+		if (K > 2) out[2] = w0 ? n.z : (w1 ? o.w : (w2 ? n.x : n.y));
+		draw += (uint32_t)K;
+#else
+#pragma unroll
+		for (int i = 0; i < K; ++i) out[i] = next_u32();
+#endif
+	}
+	__device__ __forceinline__ static float to_f32(uint32_t u) { return (float)(u >> 8) * (1.0f / 16777216.0f); }
+	__device__ __forceinline__ static double to_f64(uint32_t u) { return (double)u * (1.0 / 4294967296.0); }
 	__device__ __forceinline__ float next_f32() { return (float)(next_u32() >> 8) * (1.0f / 16777216.0f); }  // [0,1), 24 bits
 	__device__ __forceinline__ double next_f64() { return (double)next_u32() * (1.0 / 4294967296.0); }       // the oracle's value exactly
 };

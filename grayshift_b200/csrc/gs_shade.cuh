@@ -21,7 +21,11 @@ __device__ __forceinline__ f3 unit(f3 a) { float inv = rsqrtf(dot(a, a)); return
 constexpr float kPi = 3.14159265358979323846f;
 
 // ---- random helpers, util.rs:18-60 ---------------------------------------------------------------
-__device__ __forceinline__ f3 random_unit_vector(PathRng& rng) {  // util.rs:18-29 (3 draws per rejection round)
+// Two forms of the three functions that draw several numbers in a row: *_single draws them one by one, *_take takes them
+// together (PathRng::take: at most one Philox block per call site).  Same values.  Measured on the A/B harness
+// (profiles/r02_v14_rng_take.log): *_take +3.9 % on config 1 (small-scene kernels) and +3.0 % on config 5 (eight-wide kernels), but
+// -2 % on config 4, whose 96-register kernel answers any change of shape with spills -- so kTake follows the kernel variant.
+__device__ __forceinline__ f3 random_unit_vector_single(PathRng& rng) {  // util.rs:18-29 (3 draws per rejection round)
 	for (;;) {
 		float x = rng.next_f32() * 2.0f - 1.0f;
 		float y = rng.next_f32() * 2.0f - 1.0f;
@@ -30,7 +34,7 @@ __device__ __forceinline__ f3 random_unit_vector(PathRng& rng) {  // util.rs:18-
 		if (l2 < 1.0f) { float inv = rsqrtf(l2); return mk3(x * inv, y * inv, z * inv); }
 	}
 }
-__device__ __forceinline__ f3 random_cosine_direction(PathRng& rng) {  // util.rs:48-60: NOT cosine weighted (Q1): r2^(1/4)
+__device__ __forceinline__ f3 random_cosine_direction_single(PathRng& rng) {  // util.rs:48-60: NOT cosine weighted (Q1): r2^(1/4)
 	float r1 = rng.next_f32();
 	float r2 = rng.next_f32();
 	float s, c;
@@ -40,7 +44,7 @@ __device__ __forceinline__ f3 random_cosine_direction(PathRng& rng) {  // util.r
 }
 
 // ---- Camera::get_ray, camera.rs:204-226 (f64, same draws as the oracle) --------------------------
-__device__ __forceinline__ Ray get_ray(const DCamera& cam, int i, int j, PathRng& rng) {
+__device__ __forceinline__ Ray get_ray_single(const DCamera& cam, int i, int j, PathRng& rng) {
 	double offset_x = rng.next_f64() - 0.5;
 	double offset_y = rng.next_f64() - 0.5;
 	double fi = (double)i + offset_x, fj = (double)j + offset_y;
@@ -64,6 +68,65 @@ __device__ __forceinline__ Ray get_ray(const DCamera& cam, int i, int j, PathRng
 	r.time = rng.next_f64();                                  // always drawn (Q7)
 	return r;
 }
+
+__device__ __forceinline__ f3 random_unit_vector_take(PathRng& rng) {  // util.rs:18-29 (3 draws per rejection round)
+	for (;;) {
+		uint32_t u[3];
+		rng.take(u);
+		float x = PathRng::to_f32(u[0]) * 2.0f - 1.0f;
+		float y = PathRng::to_f32(u[1]) * 2.0f - 1.0f;
+		float z = PathRng::to_f32(u[2]) * 2.0f - 1.0f;
+		float l2 = x * x + y * y + z * z;
+		if (l2 < 1.0f) { float inv = rsqrtf(l2); return mk3(x * inv, y * inv, z * inv); }
+	}
+}
+__device__ __forceinline__ f3 random_cosine_direction_take(PathRng& rng) {  // util.rs:48-60: NOT cosine weighted (Q1): r2^(1/4)
+	uint32_t u[2];
+	rng.take(u);
+	float r1 = PathRng::to_f32(u[0]);
+	float r2 = PathRng::to_f32(u[1]);
+	float s, c;
+	sincospif(2.0f * r1, &s, &c);
+	float q = sqrtf(sqrtf(r2));
+	return mk3(c * q, s * q, sqrtf(1.0f - r2));
+}
+
+// ---- Camera::get_ray, camera.rs:204-226 (f64, same draws as the oracle) --------------------------
+__device__ __forceinline__ Ray get_ray_take(const DCamera& cam, int i, int j, PathRng& rng) {
+	// draws: ox, oy, [disk pairs,] time.  Without a lens the three come from one block in one go.
+	const bool lens = cam.defocus_angle > 0.0;
+	uint32_t u[3];
+	if (lens) { uint32_t u2[2]; rng.take(u2); u[0] = u2[0]; u[1] = u2[1]; u[2] = 0u; }
+	else rng.take(u);
+	double offset_x = PathRng::to_f64(u[0]) - 0.5;
+	double offset_y = PathRng::to_f64(u[1]) - 0.5;
+	double fi = (double)i + offset_x, fj = (double)j + offset_y;
+	double psx = cam.pixel00[0] + fi * cam.du[0] + fj * cam.dv[0];
+	double psy = cam.pixel00[1] + fi * cam.du[1] + fj * cam.dv[1];
+	double psz = cam.pixel00[2] + fi * cam.du[2] + fj * cam.dv[2];
+	Ray r;
+	r.ox = cam.center[0]; r.oy = cam.center[1]; r.oz = cam.center[2];
+	if (lens) {  // defocus_disk_sample: rejection in the unit disk, util.rs:36-46
+		double vx, vy;
+		for (;;) {
+			uint32_t d2[2];
+			rng.take(d2);
+			vx = PathRng::to_f64(d2[0]) * 2.0 + -1.0;
+			vy = PathRng::to_f64(d2[1]) * 2.0 + -1.0;
+			if (vx * vx + vy * vy < 1.0) break;
+		}
+		r.ox = cam.center[0] + vx * cam.disk_u[0] + vy * cam.disk_v[0];
+		r.oy = cam.center[1] + vx * cam.disk_u[1] + vy * cam.disk_v[1];
+		r.oz = cam.center[2] + vx * cam.disk_u[2] + vy * cam.disk_v[2];
+	}
+	r.dx = psx - r.ox; r.dy = psy - r.oy; r.dz = psz - r.oz;  // not normalised (Q6)
+	r.time = lens ? rng.next_f64() : PathRng::to_f64(u[2]);  // always drawn (Q7)
+	return r;
+}
+
+template <bool kTake> __device__ __forceinline__ f3 random_unit_vector(PathRng& rng) { return kTake ? random_unit_vector_take(rng) : random_unit_vector_single(rng); }
+template <bool kTake> __device__ __forceinline__ f3 random_cosine_direction(PathRng& rng) { return kTake ? random_cosine_direction_take(rng) : random_cosine_direction_single(rng); }
+template <bool kTake> __device__ __forceinline__ Ray get_ray(const DCamera& cam, int i, int j, PathRng& rng) { return kTake ? get_ray_take(cam, i, j, rng) : get_ray_single(cam, i, j, rng); }
 
 // ---- HDRI::sample, camera.rs:257-270 ----------------------------------------------------------------
 __device__ __forceinline__ f3 background(const DeviceScene& sc, const DCamera& cam, f3 d, uint32_t& tex_fetches) {
@@ -90,12 +153,22 @@ __device__ __forceinline__ f3 background(const DeviceScene& sc, const DCamera& c
 // of Perlin's Java bit trick; the oracle restates the same table).  Branch-free: the 16-way switch was inlined 8 times
 // per octave and made up a fifth of the kernel's code.  The nibble table folds 12..15 onto 0, 1, 9, 11; for h < 12
 // the gradient is (+-u) + (+-v) with u = x or y, v = y or z and the signs in bits 0 and 1.
-__device__ __forceinline__ float perlin_grad(uint32_t h, float x, float y, float z) {
+// kLut: the gradient as a vector from the CTA's table (three LDS + three FMAs; load_perm fills it) instead of the selects.
+// Same value bit for bit (one coefficient is 0, the others +-1, so the sum is (+-u) + (+-v) rounded once).  Measured
+// (profiles/r02_v14_perlin_lut.log): +20 % on the reference's Perlin scene 3 and +25 % on scene 5, but -1.7 % on config 4, whose
+// 96-register kernel pays for the loads' registers with spills; so only the small-scene kernel variants (kF & 8) use it.
+template <bool kLut>
+__device__ __forceinline__ float perlin_grad(const uint8_t* __restrict__ perm, uint32_t h, float x, float y, float z) {
+	if (kLut) {
+		const float* g = reinterpret_cast<const float*>(perm + 256) + (h & 15u);
+		return fmaf(g[0], x, fmaf(g[16], y, g[32] * z));
+	}
 	h = (uint32_t)(0xB910BA9876543210ull >> ((h & 15u) * 4u)) & 15u;
 	const float u = h < 8u ? x : y;
 	const float v = h < 4u ? y : z;
 	return ((h & 1u) ? -u : u) + ((h & 2u) ? -v : v);
 }
+template <bool kLut>
 __device__ __forceinline__ float perlin_get(const uint8_t* __restrict__ perm, double px, double py, double pz) {
 	double fx = floor(px), fy = floor(py), fz = floor(pz);
 	int cx = (int)(long long)fx, cy = (int)(long long)fy, cz = (int)(long long)fz;
@@ -103,10 +176,10 @@ __device__ __forceinline__ float perlin_get(const uint8_t* __restrict__ perm, do
 	uint32_t hx0 = perm[cx & 255], hx1 = perm[(cx + 1) & 255];
 	uint32_t y0 = (uint32_t)(cy & 255), y1 = (uint32_t)((cy + 1) & 255), z0 = (uint32_t)(cz & 255), z1 = (uint32_t)((cz + 1) & 255);
 	uint32_t h00 = perm[hx0 ^ y0], h10 = perm[hx1 ^ y0], h01 = perm[hx0 ^ y1], h11 = perm[hx1 ^ y1];
-	float g000 = perlin_grad(perm[h00 ^ z0], dx, dy, dz), g100 = perlin_grad(perm[h10 ^ z0], dx - 1.f, dy, dz);
-	float g010 = perlin_grad(perm[h01 ^ z0], dx, dy - 1.f, dz), g110 = perlin_grad(perm[h11 ^ z0], dx - 1.f, dy - 1.f, dz);
-	float g001 = perlin_grad(perm[h00 ^ z1], dx, dy, dz - 1.f), g101 = perlin_grad(perm[h10 ^ z1], dx - 1.f, dy, dz - 1.f);
-	float g011 = perlin_grad(perm[h01 ^ z1], dx, dy - 1.f, dz - 1.f), g111 = perlin_grad(perm[h11 ^ z1], dx - 1.f, dy - 1.f, dz - 1.f);
+	float g000 = perlin_grad<kLut>(perm, perm[h00 ^ z0], dx, dy, dz), g100 = perlin_grad<kLut>(perm, perm[h10 ^ z0], dx - 1.f, dy, dz);
+	float g010 = perlin_grad<kLut>(perm, perm[h01 ^ z0], dx, dy - 1.f, dz), g110 = perlin_grad<kLut>(perm, perm[h11 ^ z0], dx - 1.f, dy - 1.f, dz);
+	float g001 = perlin_grad<kLut>(perm, perm[h00 ^ z1], dx, dy, dz - 1.f), g101 = perlin_grad<kLut>(perm, perm[h10 ^ z1], dx - 1.f, dy, dz - 1.f);
+	float g011 = perlin_grad<kLut>(perm, perm[h01 ^ z1], dx, dy - 1.f, dz - 1.f), g111 = perlin_grad<kLut>(perm, perm[h11 ^ z1], dx - 1.f, dy - 1.f, dz - 1.f);
 	float a = dx * dx * dx * (dx * (dx * 6.f - 15.f) + 10.f);
 	float b = dy * dy * dy * (dy * (dy * 6.f - 15.f) + 10.f);
 	float c = dz * dz * dz * (dz * (dz * 6.f - 15.f) + 10.f);
@@ -130,6 +203,7 @@ struct Surface {
 	int sphere_index;   // is_sphere: index into sph_uvrot (an instance's RotateY, needed by sphere_uv only)
 };
 
+template <bool kLut>
 __device__ __forceinline__ f3 texture_value(const DeviceScene& sc, const uint8_t* __restrict__ perm, int tex, const Surface& s, uint32_t& tex_fetches) {
 #pragma unroll 1
 	for (int depth = 0; depth < 16; ++depth) {
@@ -178,7 +252,7 @@ __device__ __forceinline__ f3 texture_value(const DeviceScene& sc, const uint8_t
 			double sx = s.px, sy = s.py, sz = s.pz;
 #pragma unroll 1
 			for (int i = 0; i < 7; ++i) {
-				accum += weight * perlin_get(perm, sx, sy, sz);
+				accum += weight * perlin_get<kLut>(perm, sx, sy, sz);
 				weight *= 0.5f;
 				sx *= 2.0; sy *= 2.0; sz *= 2.0;
 			}
@@ -195,6 +269,7 @@ __device__ __forceinline__ f3 texture_value(const DeviceScene& sc, const uint8_t
 
 // ---- Material::emitted / scatter, material.rs:45-68, 87-102, 122-148, 165-169, 186-196 ------------
 // returns false when the path ends here (no scatter); emission is added to `emit`.
+template <int kTune>
 __device__ __forceinline__ bool shade(const DeviceScene& sc, const uint8_t* __restrict__ perm, const Surface& s, f3 d_in, PathRng& rng,
                                       f3& emit, f3& atten, f3& d_out, uint32_t& tex_fetches) {
 	const DMaterial* mp = sc.materials + s.material;
@@ -206,8 +281,8 @@ __device__ __forceinline__ bool shade(const DeviceScene& sc, const uint8_t* __re
 	// so the draw order of every material is unchanged.
 	const int kind = m0.x;
 	f3 tex = mk3(0.f, 0.f, 0.f), ruv = mk3(0.f, 0.f, 0.f);
-	if (kind == 0 || kind >= 3) tex = texture_value(sc, perm, m0.y, s, tex_fetches);
-	if (kind == 1 || kind >= 4) ruv = random_unit_vector(rng);
+	if (kind == 0 || kind >= 3) tex = texture_value<(kTune & 1) != 0>(sc, perm, m0.y, s, tex_fetches);
+	if (kind == 1 || kind >= 4) ruv = random_unit_vector<(kTune & 2) != 0>(rng);
 	switch (kind) {
 		case 0: {  // Lambertian
 			atten = tex;
@@ -216,7 +291,7 @@ __device__ __forceinline__ bool shade(const DeviceScene& sc, const uint8_t* __re
 			f3 a = fabsf(w.x) > 0.9f ? mk3(0.f, 1.f, 0.f) : mk3(1.f, 0.f, 0.f);
 			f3 v = unit(cross(w, a));
 			f3 u = cross(w, v);
-			f3 l = random_cosine_direction(rng);
+			f3 l = random_cosine_direction<(kTune & 2) != 0>(rng);
 			d_out = unit(u * l.x + v * l.y + w * l.z);
 			return true;
 		}
@@ -346,9 +421,10 @@ struct PathState {
 	__device__ __forceinline__ uint32_t pixel() const { return rng.pixel; }
 };
 
+template <int kTune = 0>
 __device__ __forceinline__ void path_begin(PathState& st, const DCamera& cam, uint64_t seed, uint32_t pixel, uint32_t sample) {
 	st.rng.start(seed, pixel, sample);
-	st.ray = get_ray(cam, (int)(pixel % (uint32_t)cam.width), (int)(pixel / (uint32_t)cam.width), st.rng);
+	st.ray = get_ray<(kTune & 2) != 0>(cam, (int)(pixel % (uint32_t)cam.width), (int)(pixel / (uint32_t)cam.width), st.rng);
 	st.L = mk3(0.f, 0.f, 0.f);
 	st.T = mk3(1.f, 1.f, 1.f);
 	st.bounce = 0;
@@ -381,7 +457,7 @@ __device__ __forceinline__ bool segment_begin(const DeviceScene& sc, const DCame
 
 // The rest of the level: miss -> background; hit -> emitted + scatter.  `h` is the closest surface hit found with
 // tmax = the medium candidate.  Returns true when the path is finished; st.L then holds the sample colour.
-template <bool kTris>
+template <bool kTris, int kTune = 0>
 __device__ __forceinline__ bool segment_shade(const DeviceScene& sc, const DCamera& cam, const uint8_t* __restrict__ perm, PathState& st,
                                               PathCounters& pc, const Hit& h, double tmax, int medium_hit) {
 	Ray& ray = st.ray;
@@ -431,7 +507,7 @@ __device__ __forceinline__ bool segment_shade(const DeviceScene& sc, const DCame
 	s.n = s.front ? n_out : -n_out;
 	s.n_out = n_out;
 	f3 emit, atten, d_out;
-	bool scattered = shade(sc, perm, s, d_in, st.rng, emit, atten, d_out, pc.tex_fetches);
+	bool scattered = shade<kTune>(sc, perm, s, d_in, st.rng, emit, atten, d_out, pc.tex_fetches);
 	st.L = st.L + st.T * emit;
 	if (!scattered) return true;
 	st.T = st.T * atten;
@@ -442,6 +518,10 @@ __device__ __forceinline__ bool segment_shade(const DeviceScene& sc, const DCame
 }
 
 // One whole level, run to completion (adaptive kernel and the per-path hooks).
+// kernel variant -> tuning of the shading code: bit 0 Perlin gradients from the CTA's table, bit 1 draws taken together.
+// Small-scene kernels (kF & 8) both, eight-wide kernels (kF & 16) the draws, the others neither (see the measurements above).
+__host__ __device__ constexpr int tune_of(int kF) { return (kF & 8) ? 3 : ((kF & 16) ? 2 : 0); }
+
 template <int kF>
 __device__ __forceinline__ bool path_step(const DeviceScene& sc, const DCamera& cam, const uint8_t* __restrict__ perm, PathState& st,
                                           PathCounters& pc) {
@@ -449,7 +529,7 @@ __device__ __forceinline__ bool path_step(const DeviceScene& sc, const DCamera& 
 	int medium_hit;
 	if (!segment_begin(sc, cam, st, pc, tmax, medium_hit)) return true;
 	Hit h = trace_closest<kF>(sc, st.ray, 0.001, tmax, &pc.node_visits);
-	return segment_shade<(kF & 2) != 0>(sc, cam, perm, st, pc, h, tmax, medium_hit);
+	return segment_shade<(kF & 2) != 0, tune_of(kF)>(sc, cam, perm, st, pc, h, tmax, medium_hit);
 }
 
 }  // namespace gs

@@ -82,11 +82,11 @@ __global__ void __launch_bounds__(kBlock, (kF & 8) ? GS_MIN_BLOCKS + 1 : GS_MIN_
 		s_rnd.total_items = (unsigned long long)__ldcg(P.n_list + (P.round0 & 1u)) * P.sample_count;
 		s_rnd.pixel_list = P.pixel_list + (size_t)(P.round0 & 1u) * P.n_pixels; s_rnd.work_counter = P.work_counter; s_rnd.round = P.round0;
 	}
-	__shared__ uint8_t s_perm[256];
+	__shared__ __align__(16) uint8_t s_perm[perm_bytes((tune_of(kF) & 1) != 0)];
 	__shared__ float4 s_top[kTopNodes > 0 ? kTopNodes * 4 : 1];
 	if (kTopNodes > 0)
 		for (int i = threadIdx.x; i < kTopNodes * 4; i += kBlock) s_top[i] = __ldg(reinterpret_cast<const float4*>(P.sc.nodes) + i);
-	load_perm(s_perm, P.sc.perlin_perm);
+	load_perm<(tune_of(kF) & 1) != 0>(s_perm, P.sc.perlin_perm);
 	const unsigned lane = threadIdx.x & 31u;
 	const unsigned lt_mask = (1u << lane) - 1u;
 	PathCounters pc = {0u, 0u, 0u};
@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(kBlock, (kF & 8) ? GS_MIN_BLOCKS + 1 : GS_MIN_
 			st.rng.k0 = (uint32_t)P.seed; st.rng.k1 = (uint32_t)(P.seed >> 32);
 			// (tv.best.t doubles as the medium's event distance: it starts as the medium candidate and only a closer
 			// surface hit lowers it)
-			if (segment_shade<(kF & 2) != 0>(P.sc, P.cam, s_perm, st, pc, tv.best, tv.best.t, seg_medium)) finish_path();
+			if (segment_shade<(kF & 2) != 0, tune_of(kF)>(P.sc, P.cam, s_perm, st, pc, tv.best, tv.best.t, seg_medium)) finish_path();
 			else state = kSetup;
 			if (!(kF & 1)) pc.tex_fetches = 0u;  // texel fetches are a statistic of the counting variant only (one register less here)
 		}
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(kBlock, (kF & 8) ? GS_MIN_BLOCKS + 1 : GS_MIN_
 						// L1 (CCTL.IVALL), so an ordinary cached load sees the new list -- a warp's lanes share a pixel, i.e. one line.
 						// (Reading it from L2 with ld.cg cost every regeneration an L2 round trip: -15 % on the final scene.)
 						if (kAdaptive) pixel = s_rnd.pixel_list[pixel];
-						path_begin(st, P.cam, P.seed, pixel, sample);
+						path_begin<tune_of(kF)>(st, P.cam, P.seed, pixel, sample);
 						state = kSetup;
 					}
 				}
@@ -417,7 +417,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 template <int kF>  // 2 = binary tree, 18 = eight-wide tree (both with the triangle branch: this kernel is not the hot one)
 __global__ void __launch_bounds__(kBlock) adaptive_tail_kernel(const __grid_constant__ AdaptiveTailParams P) {
-	__shared__ uint8_t s_perm[256];
+	__shared__ __align__(16) uint8_t s_perm[kPermBytes];
 	load_perm(s_perm, P.sc.perlin_perm);
 	const unsigned lane = threadIdx.x & 31u;
 	const unsigned lt_mask = (1u << lane) - 1u;
@@ -485,7 +485,7 @@ __global__ void __launch_bounds__(kBlock) adaptive_tail_kernel(const __grid_cons
 // done; they are not counted in the statistics (paths, rays, node visits are those of the batches kept).
 template <int kF, int kWarps>
 __global__ void __launch_bounds__(kWarps * 32) adaptive_tail_ahead_kernel(const __grid_constant__ AdaptiveTailParams P) {
-	__shared__ uint8_t s_perm[256];
+	__shared__ __align__(16) uint8_t s_perm[kPermBytes];
 	__shared__ double s_part[kWarps][5];  // per batch: sum lum, sum lum^2, r, g, b
 	__shared__ unsigned long long s_k;
 	load_perm(s_perm, P.sc.perlin_perm);
@@ -624,7 +624,7 @@ __global__ void camera_rays_kernel(const __grid_constant__ DCamera cam, unsigned
 	if (n >= pixel_end) return;
 	PathRng rng;
 	rng.start(seed, (uint32_t)n, sample);
-	Ray r = get_ray(cam, n % cam.width, n / cam.width, rng);
+	Ray r = get_ray<false>(cam, n % cam.width, n / cam.width, rng);
 	double* o = rays_out + (size_t)(n - pixel_begin) * 7;
 	o[0] = r.ox; o[1] = r.oy; o[2] = r.oz; o[3] = r.dx; o[4] = r.dy; o[5] = r.dz; o[6] = r.time;
 }
@@ -633,7 +633,7 @@ template <int kF>
 __global__ void __launch_bounds__(kBlock) path_radiance_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ DCamera cam,
                                                                unsigned long long seed, const unsigned* __restrict__ pixel,
                                                                const unsigned* __restrict__ sample, size_t n, float* __restrict__ out_rgb) {
-	__shared__ uint8_t s_perm[256];
+	__shared__ __align__(16) uint8_t s_perm[kPermBytes];
 	load_perm(s_perm, sc.perlin_perm);
 	size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (k >= n) return;

@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(kBlock) wf_classify_kernel(const __grid_consta
 
 // ---- shade -----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBlock) wf_shade_kernel(const __grid_constant__ WavefrontParams P) {
-	__shared__ uint8_t s_perm[256];
+	__shared__ __align__(16) uint8_t s_perm[kPermBytes];
 	load_perm(s_perm, P.sc.perlin_perm);
 	unsigned s = blockIdx.x * kBlock + threadIdx.x;
 	const unsigned lane = threadIdx.x & 31u;
