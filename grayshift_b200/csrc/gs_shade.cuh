@@ -191,6 +191,69 @@ __device__ __forceinline__ float perlin_get(const uint8_t* __restrict__ perm, do
 	return fminf(fmaxf(v, -1.0f), 1.0f);
 }
 
+// turb(p, 7) without the final abs (texture.rs:116-130 keeps it for the caller), by one lane
+template <bool kLut>
+__device__ __forceinline__ float noise_turb(const uint8_t* __restrict__ perm, double sx, double sy, double sz) {
+	float accum = 0.0f, weight = 1.0f;
+#pragma unroll 1
+	for (int i = 0; i < 7; ++i) {
+		accum += weight * perlin_get<kLut>(perm, sx, sy, sz);
+		weight *= 0.5f;
+		sx *= 2.0; sy *= 2.0; sz *= 2.0;
+	}
+	return accum;
+}
+
+// ---- turb(p, 7) of ONE point by the whole warp ------------------------------------------------------------------
+// The megakernel meets a NoiseTexture on ~2.5 of a warp's 32 lanes at a time (config 4: one marble sphere among 3400
+// primitives), and the serial turbulence -- 7 octaves x 8 lattice corners, ~1400 instructions -- was 8 % of its warp
+// instructions at those 2.5 lanes (profiles/r02_v13_c4_render_fixed_hotspots.txt).  Here the lane that holds the point
+// (`src`) broadcasts it and lane (octave << 2 | corner pair) evaluates the two corners (jx, jy, 0) and (jx, jy, 1) of its
+// octave, weighted with the trilinear factors of the fade curves: the octave's value is the sum over its four lanes (the
+// same interpolant as perlin_get's polynomial form, summed in another order), then scale + clamp per octave exactly
+// like perlin_get, then the sum over the octaves with the weights 2^-octave.  Lanes 28..31 idle.  All 32 lanes must call it.
+// Returns turb's `accum` on every lane.
+template <bool kLut>
+__device__ __forceinline__ float noise_turb_coop(const uint8_t* __restrict__ perm, unsigned src, double px, double py, double pz, unsigned lane) {
+	const double bx = __shfl_sync(0xffffffffu, px, src), by = __shfl_sync(0xffffffffu, py, src), bz = __shfl_sync(0xffffffffu, pz, src);
+	const unsigned o = lane >> 2, jx = lane & 1u, jy = (lane >> 1) & 1u;
+	const double mul = (double)(1u << o);  // the serial loop doubles the point per octave: exact either way
+	const double qx = bx * mul, qy = by * mul, qz = bz * mul;
+	const double fx = floor(qx), fy = floor(qy), fz = floor(qz);
+	const int cx = (int)(long long)fx, cy = (int)(long long)fy, cz = (int)(long long)fz;
+	const float dx = (float)(qx - fx), dy = (float)(qy - fy), dz = (float)(qz - fz);
+	const uint32_t hx = perm[(cx + (int)jx) & 255];
+	const uint32_t hxy = perm[hx ^ (uint32_t)((cy + (int)jy) & 255)];
+	const uint32_t h0 = perm[hxy ^ (uint32_t)(cz & 255)], h1 = perm[hxy ^ (uint32_t)((cz + 1) & 255)];
+	const float ex = dx - (float)jx, ey = dy - (float)jy;
+	const float g0 = perlin_grad<kLut>(perm, h0, ex, ey, dz), g1 = perlin_grad<kLut>(perm, h1, ex, ey, dz - 1.f);
+	const float a = dx * dx * dx * (dx * (dx * 6.f - 15.f) + 10.f);
+	const float b = dy * dy * dy * (dy * (dy * 6.f - 15.f) + 10.f);
+	const float c = dz * dz * dz * (dz * (dz * 6.f - 15.f) + 10.f);
+	const float wx = jx ? a : 1.f - a, wy = jy ? b : 1.f - b;
+	float v = wx * wy * fmaf(c, g1 - g0, g0);
+	v += __shfl_xor_sync(0xffffffffu, v, 1);
+	v += __shfl_xor_sync(0xffffffffu, v, 2);
+	v *= 1.1547005383792515f;
+	v = fminf(fmaxf(v, -1.0f), 1.0f);
+	// (after the two exchanges the four lanes of an octave hold the same v, so each residue class lane & 3 sums the octaves on its own
+	// and every lane ends with the total)
+	float t = o < 7u ? v * __uint_as_float((127u - o) << 23) : 0.0f;  // weight 2^-octave
+	t += __shfl_xor_sync(0xffffffffu, t, 4);
+	t += __shfl_xor_sync(0xffffffffu, t, 8);
+	t += __shfl_xor_sync(0xffffffffu, t, 16);
+	return t;
+}
+// NoiseTexture's value from turb's sum: 0.5 * (1 + sin(scale * z + 10 * |turb|)) (texture.rs:107-130), shared by the serial and
+// the cooperative form.
+__device__ __forceinline__ float noise_value(double scale, double pz, float accum) {
+	// sin of a phase that can reach a few hundred radians: reduce to [-pi, pi] in f64 (cheap, exact enough),
+	// then the SFU sine (abs. error ~1e-6 there); libm's sinf drags in its 280-instruction slow path
+	const double phase = scale * pz + (double)(10.0f * fabsf(accum));
+	const float red = (float)(phase - 6.283185307179586 * rint(phase * 0.15915494309189535));
+	return 0.5f * (1.0f + __sinf(red));
+}
+
 // ---- Texture::value_at, texture.rs:27-30, 57-70, 84-94, 107-130 --------------------------------------
 struct Surface {
 	double px, py, pz;  // hit position (f64: it is the next ray's origin)
@@ -203,8 +266,11 @@ struct Surface {
 	int sphere_index;   // is_sphere: index into sph_uvrot (an instance's RotateY, needed by sphere_uv only)
 };
 
-template <bool kLut>
-__device__ __forceinline__ f3 texture_value(const DeviceScene& sc, const uint8_t* __restrict__ perm, int tex, const Surface& s, uint32_t& tex_fetches) {
+// kDefer: a NoiseTexture is not evaluated here; its index is handed back in `pend` with the value (1, 1, 1), and the caller
+// evaluates it with the whole warp at its next converged point (noise_turb_coop) and multiplies the result in.
+template <bool kLut, bool kDefer = false>
+__device__ __forceinline__ f3 texture_value(const DeviceScene& sc, const uint8_t* __restrict__ perm, int tex, const Surface& s, uint32_t& tex_fetches,
+                                            int* pend = nullptr) {
 #pragma unroll 1
 	for (int depth = 0; depth < 16; ++depth) {
 		const DTexture* tp = sc.textures + tex;
@@ -246,21 +312,10 @@ __device__ __forceinline__ f3 texture_value(const DeviceScene& sc, const uint8_t
 			++tex_fetches;
 			return mk3((float)px.x * (1.0f / 255.0f), (float)px.y * (1.0f / 255.0f), (float)px.z * (1.0f / 255.0f));
 		}
+		if (kDefer) { *pend = tex; return mk3(1.f, 1.f, 1.f); }
 		{  // NoiseTexture: 0.5 * (1 + sin(scale*z + 10*turb(p, 7))) (texture.rs:107-130)
 			const double2 sd = __ldg(reinterpret_cast<const double2*>(tp) + 2);
-			float accum = 0.0f, weight = 1.0f;
-			double sx = s.px, sy = s.py, sz = s.pz;
-#pragma unroll 1
-			for (int i = 0; i < 7; ++i) {
-				accum += weight * perlin_get<kLut>(perm, sx, sy, sz);
-				weight *= 0.5f;
-				sx *= 2.0; sy *= 2.0; sz *= 2.0;
-			}
-			// sin of a phase that can reach a few hundred radians: reduce to [-pi, pi] in f64 (cheap, exact enough),
-			// then the SFU sine (abs. error ~1e-6 there); libm's sinf drags in its 280-instruction slow path
-			const double phase = sd.y * s.pz + (double)(10.0f * fabsf(accum));
-			const float red = (float)(phase - 6.283185307179586 * rint(phase * 0.15915494309189535));
-			float g = 0.5f * (1.0f + __sinf(red));
+			const float g = noise_value(sd.y, s.pz, noise_turb<kLut>(perm, s.px, s.py, s.pz));
 			return mk3(g, g, g);
 		}
 	}
@@ -269,9 +324,11 @@ __device__ __forceinline__ f3 texture_value(const DeviceScene& sc, const uint8_t
 
 // ---- Material::emitted / scatter, material.rs:45-68, 87-102, 122-148, 165-169, 186-196 ------------
 // returns false when the path ends here (no scatter); emission is added to `emit`.
+// kTune bit 2: NoiseTextures are deferred (texture_value's kDefer).  `pend` = -1, or (texture index << 1 | 1 when the value is
+// an emission, 0 when it is an attenuation); the deferred factor enters as 1 (attenuation) or 0 (emission) here.
 template <int kTune>
 __device__ __forceinline__ bool shade(const DeviceScene& sc, const uint8_t* __restrict__ perm, const Surface& s, f3 d_in, PathRng& rng,
-                                      f3& emit, f3& atten, f3& d_out, uint32_t& tex_fetches) {
+                                      f3& emit, f3& atten, f3& d_out, uint32_t& tex_fetches, int& pend) {
 	const DMaterial* mp = sc.materials + s.material;
 	const int4 m0 = __ldg(reinterpret_cast<const int4*>(mp));        // kind, tex, albedo.r, albedo.g
 	const float4 m1 = __ldg(reinterpret_cast<const float4*>(mp) + 1);  // albedo.b, param
@@ -281,7 +338,14 @@ __device__ __forceinline__ bool shade(const DeviceScene& sc, const uint8_t* __re
 	// so the draw order of every material is unchanged.
 	const int kind = m0.x;
 	f3 tex = mk3(0.f, 0.f, 0.f), ruv = mk3(0.f, 0.f, 0.f);
-	if (kind == 0 || kind >= 3) tex = texture_value<(kTune & 1) != 0>(sc, perm, m0.y, s, tex_fetches);
+	constexpr bool kDefer = (kTune & 4) != 0;
+	int noise = -1;
+	if (kind == 0 || kind >= 3) tex = texture_value<(kTune & 1) != 0, kDefer>(sc, perm, m0.y, s, tex_fetches, &noise);
+	pend = -1;
+	if (kDefer && noise >= 0) {
+		pend = (noise << 1) | (kind == 3 ? 1 : 0);
+		if (kind == 3) tex = mk3(0.f, 0.f, 0.f);
+	}
 	if (kind == 1 || kind >= 4) ruv = random_unit_vector<(kTune & 2) != 0>(rng);
 	switch (kind) {
 		case 0: {  // Lambertian
@@ -457,9 +521,11 @@ __device__ __forceinline__ bool segment_begin(const DeviceScene& sc, const DCame
 
 // The rest of the level: miss -> background; hit -> emitted + scatter.  `h` is the closest surface hit found with
 // tmax = the medium candidate.  Returns true when the path is finished; st.L then holds the sample colour.
+// kTune bit 2 (the megakernel): a NoiseTexture met here is left to the caller -- `*pend` as shade() describes it, the point
+// in st.ray's origin; see noise_apply_deferred.
 template <bool kTris, int kTune = 0>
 __device__ __forceinline__ bool segment_shade(const DeviceScene& sc, const DCamera& cam, const uint8_t* __restrict__ perm, PathState& st,
-                                              PathCounters& pc, const Hit& h, double tmax, int medium_hit) {
+                                              PathCounters& pc, const Hit& h, double tmax, int medium_hit, int* pend = nullptr) {
 	Ray& ray = st.ray;
 	f3 d_in = mk3((float)ray.dx, (float)ray.dy, (float)ray.dz);
 	if (h.ref == kNoHit && medium_hit < 0) {  // sample_background, camera.rs:228-233
@@ -507,14 +573,49 @@ __device__ __forceinline__ bool segment_shade(const DeviceScene& sc, const DCame
 	s.n = s.front ? n_out : -n_out;
 	s.n_out = n_out;
 	f3 emit, atten, d_out;
-	bool scattered = shade<kTune>(sc, perm, s, d_in, st.rng, emit, atten, d_out, pc.tex_fetches);
+	int noise;
+	bool scattered = shade<kTune>(sc, perm, s, d_in, st.rng, emit, atten, d_out, pc.tex_fetches, noise);
+	if (kTune & 4) *pend = noise;
 	st.L = st.L + st.T * emit;
-	if (!scattered) return true;
+	if (!scattered) {
+		if ((kTune & 4) && noise >= 0) { ray.ox = s.px; ray.oy = s.py; ray.oz = s.pz; }  // the deferred evaluation reads the point here
+		return true;
+	}
 	st.T = st.T * atten;
 	ray.ox = s.px; ray.oy = s.py; ray.oz = s.pz;
 	ray.dx = (double)d_out.x; ray.dy = (double)d_out.y; ray.dz = (double)d_out.z;
 	++st.bounce;
 	return false;
+}
+
+#ifndef GS_NOISE_COOP_MAX
+#define GS_NOISE_COOP_MAX 8  // pending lanes up to which the warp serves them together, one after the other (~100 instructions each,
+                             // against ~1400 -- ~700 with the gradient table -- for any number of lanes evaluating on their own)
+#endif
+// The deferred NoiseTextures of a warp (segment_shade with kTune bit 2), at a converged point: every lane passes its `pend`
+// (-1 = nothing) and its path state; the pending lanes are served one after the other by all 32 lanes, and the value is
+// multiplied in where the serial code would have used it: T *= g (Lambertian / Isotropic albedo) or L += T * g (DiffuseLight).
+template <bool kLut>
+__device__ __forceinline__ void noise_apply_deferred(const DeviceScene& sc, const uint8_t* __restrict__ perm, PathState& st, int pend, unsigned lane) {
+	unsigned todo = __ballot_sync(0xffffffffu, pend >= 0);
+	if (todo == 0u) return;
+	float accum = 0.0f;
+	if (GS_NOISE_COOP_MAX < 32 && __popc(todo) > GS_NOISE_COOP_MAX) {  // a warp full of marble (the reference's Perlin scenes): each lane for itself is cheaper
+		if (pend >= 0) accum = noise_turb<kLut>(perm, st.ray.ox, st.ray.oy, st.ray.oz);
+	} else {
+		do {
+			const unsigned src = __ffs(todo) - 1u;
+			todo &= todo - 1u;
+			const float a = noise_turb_coop<kLut>(perm, src, st.ray.ox, st.ray.oy, st.ray.oz, lane);
+			if (lane == src) accum = a;
+		} while (todo);
+	}
+	if (pend >= 0) {
+		const double2 sd = __ldg(reinterpret_cast<const double2*>(sc.textures + (pend >> 1)) + 2);
+		const float g = noise_value(sd.y, st.ray.oz, accum);
+		if (pend & 1) st.L = st.L + st.T * mk3(g, g, g);
+		else st.T = st.T * mk3(g, g, g);
+	}
 }
 
 // One whole level, run to completion (adaptive kernel and the per-path hooks).

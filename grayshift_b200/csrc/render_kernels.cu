@@ -54,6 +54,9 @@ static_assert(kTopNodes <= kNodePad, "gs_scene_create pads the node array to kNo
 #define GS_MIN_SHADE_WIDE 20  // the same threshold in the kernels that walk the eight-wide tree: a wide node step costs three times a binary one,
                               // so waiting for the 24th ray is dearer there (16 / 20 / 24: 386.9 / 388.4 / 377.2 M paths/s on config 5, profiles/r02_v6_variants.log)
 #endif
+#ifndef GS_NOISE_COOP
+#define GS_NOISE_COOP 1   // NoiseTextures are evaluated by the whole warp after the shading phase (noise_turb_coop); 0 = by the lane that met one
+#endif
 #ifndef GS_BAIL
 #define GS_BAIL 6         // resumable traversal: the node loop of a round ends once no more than this many lanes still descend
 #endif
@@ -70,8 +73,13 @@ constexpr int kBail = GS_BAIL;
 // gs_scene_create: a large scene's binary nodes come from L2 and every fetch is a dependent round trip
 // bit 3 = the scene's nodes and primitives fit the L1 several times over: one more CTA per SM (80 registers, some spills into the
 // shading code) -- measured +3...4 % on C1 / C3 and -3 % on C4, whose 0.5 MB working set feels the spills in the L1
+#ifdef GS_MAXNREG
+#define GS_RENDER_BOUNDS(kF) __maxnreg__(GS_MAXNREG)  // A/B builds: an explicit register cap instead of the CTA count
+#else
+#define GS_RENDER_BOUNDS(kF) __launch_bounds__(kBlock, ((kF) & 8) ? GS_MIN_BLOCKS + 1 : GS_MIN_BLOCKS)
+#endif
 template <int kF>
-__global__ void __launch_bounds__(kBlock, (kF & 8) ? GS_MIN_BLOCKS + 1 : GS_MIN_BLOCKS) render_fixed_kernel(const __grid_constant__ RenderParams P) {
+__global__ void GS_RENDER_BOUNDS(kF) render_fixed_kernel(const __grid_constant__ RenderParams P) {
 	constexpr bool kAdaptive = (kF & 4) != 0;
 	using Trav = typename std::conditional<(kF & 16) != 0, Trav8, Trav2>::type;
 	// adaptive: one iteration of the round loop below per batch.  What changes from round to round is CTA-uniform and lives in
@@ -89,6 +97,7 @@ __global__ void __launch_bounds__(kBlock, (kF & 8) ? GS_MIN_BLOCKS + 1 : GS_MIN_
 	load_perm<(tune_of(kF) & 1) != 0>(s_perm, P.sc.perlin_perm);
 	const unsigned lane = threadIdx.x & 31u;
 	const unsigned lt_mask = (1u << lane) - 1u;
+	constexpr int kShadeTune = tune_of(kF) | (GS_NOISE_COOP ? 4 : 0);
 	PathCounters pc = {0u, 0u, 0u};
 	PathState st;
 	int state = kDead;
@@ -142,14 +151,21 @@ __global__ void __launch_bounds__(kBlock, (kF & 8) ? GS_MIN_BLOCKS + 1 : GS_MIN_
 	for (;;) {  // rounds of the adaptive sampler (the fixed-count kernels leave after the first)
 	for (;;) {
 		// ---- phase A1: shade the lanes whose traversal finished --------------------------------------
+		bool finished = false;
+		int noise_pend = -1;
 		if (state == kShade) {
 			// the RNG key is a kernel parameter: re-reading it here ends the live range of two registers before phase B
 			st.rng.k0 = (uint32_t)P.seed; st.rng.k1 = (uint32_t)(P.seed >> 32);
 			// (tv.best.t doubles as the medium's event distance: it starts as the medium candidate and only a closer
 			// surface hit lowers it)
-			if (segment_shade<(kF & 2) != 0, tune_of(kF)>(P.sc, P.cam, s_perm, st, pc, tv.best, tv.best.t, seg_medium)) finish_path();
-			else state = kSetup;
+			finished = segment_shade<(kF & 2) != 0, kShadeTune>(P.sc, P.cam, s_perm, st, pc, tv.best, tv.best.t, seg_medium, &noise_pend);
 			if (!(kF & 1)) pc.tex_fetches = 0u;  // texel fetches are a statistic of the counting variant only (one register less here)
+		}
+		// NoiseTextures met in this phase: evaluated here by the whole warp, one pending lane after the other (gs_shade.cuh)
+		if (kShadeTune & 4) noise_apply_deferred<(kShadeTune & 1) != 0>(P.sc, s_perm, st, noise_pend, lane);
+		if (state == kShade) {
+			if (finished) finish_path();
+			else state = kSetup;
 		}
 		// ---- phase A2: dead lanes take the next (pixel, sample) items ------------------------------------
 		const unsigned dead = __ballot_sync(kFull, state == kDead);
