@@ -198,6 +198,49 @@ struct PathRng {
 	__device__ __forceinline__ static double to_f64(uint32_t u) { return (double)u * (1.0 / 4294967296.0); }
 	__device__ __forceinline__ float next_f32() { return (float)(next_u32() >> 8) * (1.0f / 16777216.0f); }  // [0,1), 24 bits
 	__device__ __forceinline__ double next_f64() { return (double)next_u32() * (1.0 / 4294967296.0); }       // the oracle's value exactly
+	__device__ __forceinline__ void ensure(int) {}  // blocks are computed where a draw needs one (see PathRngW)
+};
+
+// The same stream -- draw k of a path is word k & 3 of block k >> 2 -- with the blocks computed AHEAD, at a point where the warp's
+// lanes are together, instead of at whichever of a dozen divergent draw sites a lane's counter happens to cross a block boundary
+// (config 4, profiles/r02_v13: the Philox rounds and the word selection were 11 % of the megakernel's warp instructions at 12 active
+// lanes).  A lane keeps a window of two blocks in shared memory, win[(k & 7) * kStride] = word of draw k for the blocks `top - 1` and
+// `top` (win[8 * kStride] = top); a draw is one shared-memory load, and ensure(n) computes blocks until n more draws are covered.
+// Two blocks hold at least five draws past any counter, so ensure(n <= 5) can always be met.  The megakernel calls ensure(5) once
+// per level, after the media draws of segment_begin (all lanes with a fresh ray are there): enough for the first round of any
+// material (<= 3 draws) plus two media draws of the next level; rejection loops and a third medium call it again before they draw more.
+template <int kStride>
+struct PathRngW {
+	uint32_t pixel, sample, draw, k0, k1;
+	uint32_t* win;  // this thread's column of the CTA's window array [9][kStride]
+	__device__ __forceinline__ void ensure(int n) {
+		int top = (int)win[8 * kStride];
+		if ((top + 1) * 4 - (int)draw >= n) return;
+		do {
+			++top;
+			const uint4 b = philox4x32_10(pixel, sample, (uint32_t)top, 0u, k0, k1);
+			uint32_t* const w = win + (top & 1) * (4 * kStride);
+			w[0] = b.x; w[kStride] = b.y; w[2 * kStride] = b.z; w[3 * kStride] = b.w;
+		} while ((top + 1) * 4 - (int)draw < n);
+		win[8 * kStride] = (uint32_t)top;
+	}
+	__device__ __forceinline__ void start(uint64_t seed, uint32_t pixel_, uint32_t sample_) {
+		pixel = pixel_; sample = sample_; draw = 0; k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32);
+		win[8 * kStride] = 0xffffffffu;  // top = -1: nothing computed
+		ensure(5);                       // blocks 0 and 1: the camera ray (3 draws; 2 + a first lens pair + 1 with a lens) and two media
+	}
+	__device__ __forceinline__ uint32_t next_u32() {
+		const uint32_t v = win[(draw & 7u) * kStride];
+		++draw;
+		return v;
+	}
+	template <int K>
+	__device__ __forceinline__ void take(uint32_t (&out)[K]) {
+#pragma unroll
+		for (int i = 0; i < K; ++i) out[i] = next_u32();
+	}
+	__device__ __forceinline__ float next_f32() { return PathRng::to_f32(next_u32()); }
+	__device__ __forceinline__ double next_f64() { return PathRng::to_f64(next_u32()); }
 };
 
 // ------------------------------------------------------------------------------------------

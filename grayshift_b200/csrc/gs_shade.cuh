@@ -25,16 +25,19 @@ constexpr float kPi = 3.14159265358979323846f;
 // together (PathRng::take: at most one Philox block per call site).  Same values.  Measured on the A/B harness
 // (profiles/r02_v14_rng_take.log): *_take +3.9 % on config 1 (small-scene kernels) and +3.0 % on config 5 (eight-wide kernels), but
 // -2 % on config 4, whose 96-register kernel answers any change of shape with spills -- so kTake follows the kernel variant.
-__device__ __forceinline__ f3 random_unit_vector_single(PathRng& rng) {  // util.rs:18-29 (3 draws per rejection round)
+template <class Rng>
+__device__ __forceinline__ f3 random_unit_vector_single(Rng& rng) {  // util.rs:18-29 (3 draws per rejection round)
 	for (;;) {
 		float x = rng.next_f32() * 2.0f - 1.0f;
 		float y = rng.next_f32() * 2.0f - 1.0f;
 		float z = rng.next_f32() * 2.0f - 1.0f;
 		float l2 = x * x + y * y + z * z;
 		if (l2 < 1.0f) { float inv = rsqrtf(l2); return mk3(x * inv, y * inv, z * inv); }
+		rng.ensure(5);  // another round, and two media draws after it
 	}
 }
-__device__ __forceinline__ f3 random_cosine_direction_single(PathRng& rng) {  // util.rs:48-60: NOT cosine weighted (Q1): r2^(1/4)
+template <class Rng>
+__device__ __forceinline__ f3 random_cosine_direction_single(Rng& rng) {  // util.rs:48-60: NOT cosine weighted (Q1): r2^(1/4)
 	float r1 = rng.next_f32();
 	float r2 = rng.next_f32();
 	float s, c;
@@ -44,7 +47,8 @@ __device__ __forceinline__ f3 random_cosine_direction_single(PathRng& rng) {  //
 }
 
 // ---- Camera::get_ray, camera.rs:204-226 (f64, same draws as the oracle) --------------------------
-__device__ __forceinline__ Ray get_ray_single(const DCamera& cam, int i, int j, PathRng& rng) {
+template <class Rng>
+__device__ __forceinline__ Ray get_ray_single(const DCamera& cam, int i, int j, Rng& rng) {
 	double offset_x = rng.next_f64() - 0.5;
 	double offset_y = rng.next_f64() - 0.5;
 	double fi = (double)i + offset_x, fj = (double)j + offset_y;
@@ -59,6 +63,7 @@ __device__ __forceinline__ Ray get_ray_single(const DCamera& cam, int i, int j, 
 			vx = rng.next_f64() * 2.0 + -1.0;
 			vy = rng.next_f64() * 2.0 + -1.0;
 			if (vx * vx + vy * vy < 1.0) break;
+			rng.ensure(5);  // another pair, the time, and two media draws
 		}
 		r.ox = cam.center[0] + vx * cam.disk_u[0] + vy * cam.disk_v[0];
 		r.oy = cam.center[1] + vx * cam.disk_u[1] + vy * cam.disk_v[1];
@@ -69,7 +74,8 @@ __device__ __forceinline__ Ray get_ray_single(const DCamera& cam, int i, int j, 
 	return r;
 }
 
-__device__ __forceinline__ f3 random_unit_vector_take(PathRng& rng) {  // util.rs:18-29 (3 draws per rejection round)
+template <class Rng>
+__device__ __forceinline__ f3 random_unit_vector_take(Rng& rng) {  // util.rs:18-29 (3 draws per rejection round)
 	for (;;) {
 		uint32_t u[3];
 		rng.take(u);
@@ -78,9 +84,11 @@ __device__ __forceinline__ f3 random_unit_vector_take(PathRng& rng) {  // util.r
 		float z = PathRng::to_f32(u[2]) * 2.0f - 1.0f;
 		float l2 = x * x + y * y + z * z;
 		if (l2 < 1.0f) { float inv = rsqrtf(l2); return mk3(x * inv, y * inv, z * inv); }
+		rng.ensure(5);  // another round, and two media draws after it
 	}
 }
-__device__ __forceinline__ f3 random_cosine_direction_take(PathRng& rng) {  // util.rs:48-60: NOT cosine weighted (Q1): r2^(1/4)
+template <class Rng>
+__device__ __forceinline__ f3 random_cosine_direction_take(Rng& rng) {  // util.rs:48-60: NOT cosine weighted (Q1): r2^(1/4)
 	uint32_t u[2];
 	rng.take(u);
 	float r1 = PathRng::to_f32(u[0]);
@@ -92,7 +100,8 @@ __device__ __forceinline__ f3 random_cosine_direction_take(PathRng& rng) {  // u
 }
 
 // ---- Camera::get_ray, camera.rs:204-226 (f64, same draws as the oracle) --------------------------
-__device__ __forceinline__ Ray get_ray_take(const DCamera& cam, int i, int j, PathRng& rng) {
+template <class Rng>
+__device__ __forceinline__ Ray get_ray_take(const DCamera& cam, int i, int j, Rng& rng) {
 	// draws: ox, oy, [disk pairs,] time.  Without a lens the three come from one block in one go.
 	const bool lens = cam.defocus_angle > 0.0;
 	uint32_t u[3];
@@ -114,6 +123,7 @@ __device__ __forceinline__ Ray get_ray_take(const DCamera& cam, int i, int j, Pa
 			vx = PathRng::to_f64(d2[0]) * 2.0 + -1.0;
 			vy = PathRng::to_f64(d2[1]) * 2.0 + -1.0;
 			if (vx * vx + vy * vy < 1.0) break;
+			rng.ensure(5);  // another pair, the time, and two media draws
 		}
 		r.ox = cam.center[0] + vx * cam.disk_u[0] + vy * cam.disk_v[0];
 		r.oy = cam.center[1] + vx * cam.disk_u[1] + vy * cam.disk_v[1];
@@ -124,9 +134,9 @@ __device__ __forceinline__ Ray get_ray_take(const DCamera& cam, int i, int j, Pa
 	return r;
 }
 
-template <bool kTake> __device__ __forceinline__ f3 random_unit_vector(PathRng& rng) { return kTake ? random_unit_vector_take(rng) : random_unit_vector_single(rng); }
-template <bool kTake> __device__ __forceinline__ f3 random_cosine_direction(PathRng& rng) { return kTake ? random_cosine_direction_take(rng) : random_cosine_direction_single(rng); }
-template <bool kTake> __device__ __forceinline__ Ray get_ray(const DCamera& cam, int i, int j, PathRng& rng) { return kTake ? get_ray_take(cam, i, j, rng) : get_ray_single(cam, i, j, rng); }
+template <bool kTake, class Rng> __device__ __forceinline__ f3 random_unit_vector(Rng& rng) { return kTake ? random_unit_vector_take(rng) : random_unit_vector_single(rng); }
+template <bool kTake, class Rng> __device__ __forceinline__ f3 random_cosine_direction(Rng& rng) { return kTake ? random_cosine_direction_take(rng) : random_cosine_direction_single(rng); }
+template <bool kTake, class Rng> __device__ __forceinline__ Ray get_ray(const DCamera& cam, int i, int j, Rng& rng) { return kTake ? get_ray_take(cam, i, j, rng) : get_ray_single(cam, i, j, rng); }
 
 // ---- HDRI::sample, camera.rs:257-270 ----------------------------------------------------------------
 __device__ __forceinline__ f3 background(const DeviceScene& sc, const DCamera& cam, f3 d, uint32_t& tex_fetches) {
@@ -326,8 +336,8 @@ __device__ __forceinline__ f3 texture_value(const DeviceScene& sc, const uint8_t
 // returns false when the path ends here (no scatter); emission is added to `emit`.
 // kTune bit 2: NoiseTextures are deferred (texture_value's kDefer).  `pend` = -1, or (texture index << 1 | 1 when the value is
 // an emission, 0 when it is an attenuation); the deferred factor enters as 1 (attenuation) or 0 (emission) here.
-template <int kTune>
-__device__ __forceinline__ bool shade(const DeviceScene& sc, const uint8_t* __restrict__ perm, const Surface& s, f3 d_in, PathRng& rng,
+template <int kTune, class Rng>
+__device__ __forceinline__ bool shade(const DeviceScene& sc, const uint8_t* __restrict__ perm, const Surface& s, f3 d_in, Rng& rng,
                                       f3& emit, f3& atten, f3& d_out, uint32_t& tex_fetches, int& pend) {
 	const DMaterial* mp = sc.materials + s.material;
 	const int4 m0 = __ldg(reinterpret_cast<const int4*>(mp));        // kind, tex, albedo.r, albedo.g
@@ -477,16 +487,18 @@ __device__ __forceinline__ bool medium_event(const DeviceScene& sc, const DMediu
 // ---- Camera::ray_color, camera.rs:174-202, iterative: L = sum_k (prod_{j<k} att_j) E_k (+ background) ---
 struct PathCounters { uint32_t rays, tex_fetches, node_visits; };
 
-struct PathState {
+template <class Rng>
+struct PathStateT {
 	Ray ray;
 	f3 L, T;
-	PathRng rng;
+	Rng rng;
 	unsigned bounce;
 	__device__ __forceinline__ uint32_t pixel() const { return rng.pixel; }
 };
+using PathState = PathStateT<PathRng>;
 
-template <int kTune = 0>
-__device__ __forceinline__ void path_begin(PathState& st, const DCamera& cam, uint64_t seed, uint32_t pixel, uint32_t sample) {
+template <int kTune = 0, class PS>
+__device__ __forceinline__ void path_begin(PS& st, const DCamera& cam, uint64_t seed, uint32_t pixel, uint32_t sample) {
 	st.rng.start(seed, pixel, sample);
 	st.ray = get_ray<(kTune & 2) != 0>(cam, (int)(pixel % (uint32_t)cam.width), (int)(pixel / (uint32_t)cam.width), st.rng);
 	st.L = mk3(0.f, 0.f, 0.f);
@@ -496,7 +508,8 @@ __device__ __forceinline__ void path_begin(PathState& st, const DCamera& cam, ui
 
 // Start of one level of the reference's recursion: the depth test (camera.rs:175) and the media.  Returns false
 // when the path is finished (depth exhausted).  tmax = the closest medium event (or f64::MAX), medium_hit its index.
-__device__ __forceinline__ bool segment_begin(const DeviceScene& sc, const DCamera& cam, PathState& st, PathCounters& pc, double& tmax,
+template <class PS>
+__device__ __forceinline__ bool segment_begin(const DeviceScene& sc, const DCamera& cam, PS& st, PathCounters& pc, double& tmax,
                                               int& medium_hit) {
 	if (st.bounce >= cam.max_depth) return false;  // `if depth <= 0 { return ZERO }`
 	++pc.rays;
@@ -511,11 +524,13 @@ __device__ __forceinline__ bool segment_begin(const DeviceScene& sc, const DCame
 		// happens to be; a free-flight draw is independent of everything else).  A separate stream for the media cost one
 		// more Philox block per level: a third of all Philox work on C4.
 		for (int mi = 0; mi < sc.n_media; ++mi) {
+			if (mi >= 2) st.rng.ensure(1);  // (PathRngW: two media draws are covered by the level before)
 			const float u01 = st.rng.next_f32();
 			double tm;
 			if (medium_event(sc, sc.media[mi], ray, a, inv_a, 0.001, tmax, u01, tm)) { tmax = tm; medium_hit = mi; }
 		}
 	}
+	st.rng.ensure(5);  // PathRngW: the blocks for this level's scatter and the next level's media, computed here for all lanes at once
 	return true;
 }
 
@@ -523,8 +538,8 @@ __device__ __forceinline__ bool segment_begin(const DeviceScene& sc, const DCame
 // tmax = the medium candidate.  Returns true when the path is finished; st.L then holds the sample colour.
 // kTune bit 2 (the megakernel): a NoiseTexture met here is left to the caller -- `*pend` as shade() describes it, the point
 // in st.ray's origin; see noise_apply_deferred.
-template <bool kTris, int kTune = 0>
-__device__ __forceinline__ bool segment_shade(const DeviceScene& sc, const DCamera& cam, const uint8_t* __restrict__ perm, PathState& st,
+template <bool kTris, int kTune = 0, class PS>
+__device__ __forceinline__ bool segment_shade(const DeviceScene& sc, const DCamera& cam, const uint8_t* __restrict__ perm, PS& st,
                                               PathCounters& pc, const Hit& h, double tmax, int medium_hit, int* pend = nullptr) {
 	Ray& ray = st.ray;
 	f3 d_in = mk3((float)ray.dx, (float)ray.dy, (float)ray.dz);
@@ -595,8 +610,8 @@ __device__ __forceinline__ bool segment_shade(const DeviceScene& sc, const DCame
 // The deferred NoiseTextures of a warp (segment_shade with kTune bit 2), at a converged point: every lane passes its `pend`
 // (-1 = nothing) and its path state; the pending lanes are served one after the other by all 32 lanes, and the value is
 // multiplied in where the serial code would have used it: T *= g (Lambertian / Isotropic albedo) or L += T * g (DiffuseLight).
-template <bool kLut>
-__device__ __forceinline__ void noise_apply_deferred(const DeviceScene& sc, const uint8_t* __restrict__ perm, PathState& st, int pend, unsigned lane) {
+template <bool kLut, class PS>
+__device__ __forceinline__ void noise_apply_deferred(const DeviceScene& sc, const uint8_t* __restrict__ perm, PS& st, int pend, unsigned lane) {
 	unsigned todo = __ballot_sync(0xffffffffu, pend >= 0);
 	if (todo == 0u) return;
 	float accum = 0.0f;

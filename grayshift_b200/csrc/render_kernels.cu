@@ -14,6 +14,9 @@
 // Grids are sized to SM count x resident CTAs (persistent), never to the image.
 #include <cooperative_groups.h>
 
+#include <atomic>
+#include <cstdlib>
+
 #include "gs_internal.h"
 #include "gs_kernel_util.cuh"
 
@@ -57,6 +60,13 @@ static_assert(kTopNodes <= kNodePad, "gs_scene_create pads the node array to kNo
 #ifndef GS_NOISE_COOP
 #define GS_NOISE_COOP 1   // NoiseTextures are evaluated by the whole warp after the shading phase (noise_turb_coop); 0 = by the lane that met one
 #endif
+#ifndef GS_RNG_WINDOW
+#define GS_RNG_WINDOW 0   // the megakernel's paths draw from a two-block window in shared memory, filled once per level at a converged point
+                          // (PathRngW, gs_device.cuh); 0 = one block in registers, computed at the draw that needs it
+#endif
+#ifndef GS_NODE_UNROLL2
+#define GS_NODE_UNROLL2 0
+#endif
 #ifndef GS_BAIL
 #define GS_BAIL 6         // resumable traversal: the node loop of a round ends once no more than this many lanes still descend
 #endif
@@ -99,7 +109,13 @@ __global__ void GS_RENDER_BOUNDS(kF) render_fixed_kernel(const __grid_constant__
 	const unsigned lt_mask = (1u << lane) - 1u;
 	constexpr int kShadeTune = tune_of(kF) | (GS_NOISE_COOP ? 4 : 0);
 	PathCounters pc = {0u, 0u, 0u};
+#if GS_RNG_WINDOW
+	__shared__ uint32_t s_rng[9][kBlock];  // PathRngW: two Philox blocks per lane + the index of the newer one (4.5 KB per CTA)
+	PathStateT<PathRngW<kBlock>> st;
+	st.rng.win = &s_rng[0][threadIdx.x];
+#else
 	PathState st;
+#endif
 	int state = kDead;
 	Trav tv;
 	tv.park();
@@ -292,8 +308,17 @@ __global__ void GS_RENDER_BOUNDS(kF) render_fixed_kernel(const __grid_constant__
 			// phase and carry on in the next round.  (A fully converged loop with two ballots per node step was measured
 			// 10-15 % slower than the classic loop: 12 more instructions per step, and ptxas spilled the ray constants.)
 			if (trav && tv.wants_node()) {
+#if GS_NODE_UNROLL2
+				// two node steps per look at the lanes left (the vote + count + branch are 4 of a step's 58 instructions)
+				do {
+					tv.template node_step<(kF & 1) != 0, kTopNodes>(P.sc, rc, stack, &pc.node_visits, s_top);
+					if (!tv.wants_node()) break;
+					tv.template node_step<(kF & 1) != 0, kTopNodes>(P.sc, rc, stack, &pc.node_visits, s_top);
+				} while (tv.wants_node() && __popc(__activemask()) > kBail);
+#else
 				do tv.template node_step<(kF & 1) != 0, kTopNodes>(P.sc, rc, stack, &pc.node_visits, s_top);
 				while (tv.wants_node() && __popc(__activemask()) > kBail);
+#endif
 			}
 			__syncwarp();
 			const bool leaf = trav && tv.wants_leaf();
@@ -672,15 +697,45 @@ static int fixed_variant(const RenderParams& p, bool count_nodes, bool triangles
 	return (triangles ? 2 : 0) | small | wide;
 }
 
+// Shared-memory carve-out of a render kernel: exactly what its resident CTAs need, so that the rest of the SM's 256 KB is L1.
+// Left alone the driver reserves more (the hint that reproduces its choice is 12-15 % of the maximum; the 5 CTAs x (2.9 KB + 1 KB
+// reserved) of the config-4 kernel are 8.5 %): config 4, whose 0.5 MB of nodes and primitives do not fit the L1, gains 1.3 %
+// (1701 vs 1680 M paths/s, profiles/r02_v15_carveout.log); scenes that fit are unchanged.  GS_CARVEOUT (percent) overrides.
+template <class K>
+static void set_carveout(K kernel, int blocks_per_sm) {
+	static const int forced = [] { const char* e = std::getenv("GS_CARVEOUT"); return e ? std::atoi(e) : -1; }();
+	int dev = 0, max_smem = 0, reserved = 0;
+	cudaFuncAttributes fa;
+	if (cudaGetDevice(&dev) != cudaSuccess || cudaFuncGetAttributes(&fa, kernel) != cudaSuccess) { cudaGetLastError(); return; }
+	cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+	cudaDeviceGetAttribute(&reserved, cudaDevAttrReservedSharedMemoryPerBlock, dev);
+	if (max_smem <= 0) return;
+	const long long need = (long long)blocks_per_sm * ((long long)fa.sharedSizeBytes + reserved);
+	int pct = (int)((need * 100 + max_smem - 1) / max_smem);
+	if (pct > 100) pct = 100;
+	cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, forced >= 0 ? forced : pct);
+}
+
 static int fixed_blocks_per_sm(int variant) {
+	constexpr int kMaxDev = 64;
+	static std::atomic<int> cached[kMaxDev][32];  // blocks per SM of (device, variant), 0 = not asked yet; the carve-out is set on the first ask
+	int dev = 0;
+	cudaGetDevice(&dev);
+	const bool cache = dev >= 0 && dev < kMaxDev && variant >= 0 && variant < 32;
+	if (cache) { const int c = cached[dev][variant].load(std::memory_order_acquire); if (c > 0) return c; }
 	int n = 0;
 	switch (variant) {
-#define X(v) case v: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, render_fixed_kernel<v>, kBlock, 0); break;
+#define X(v) case v: \
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, render_fixed_kernel<v>, kBlock, 0); \
+		if (n > 0) { set_carveout(render_fixed_kernel<v>, n); int m = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&m, render_fixed_kernel<v>, kBlock, 0); if (m > 0 && m < n) n = m; } \
+		break;
 		GS_FIXED_VARIANTS(X)
 #undef X
 		default: break;
 	}
-	return n > 0 ? n : 1;
+	if (n <= 0) n = 1;
+	if (cache) cached[dev][variant].store(n, std::memory_order_release);
+	return n;
 }
 
 int render_fixed_blocks_per_sm(bool count_nodes, bool triangles) { return fixed_blocks_per_sm((count_nodes ? 1 : 0) | (triangles ? 2 : 0)); }
