@@ -156,15 +156,40 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
 	return make_uint4(c0, c1, c2, c3);
 }
 
-struct PathRng {
+// The same ten rounds with the round keys (k0 + r * 0x9E3779B9, k1 + r * 0xBB67AE85) read from `rk`: when that is the kernel's
+// parameter block (RenderParams::philox_rk, filled by launch_render_fixed) each key is a constant-bank operand of the round's
+// three-input XOR, and a round is four instructions -- two wide multiplies, two XORs -- with no key arithmetic and no loop.
+__device__ __forceinline__ uint4 philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const uint32_t* __restrict__ rk) {
+#pragma unroll
+	for (int r = 0; r < 10; ++r) {
+		uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+		uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+		uint32_t n0 = hi1 ^ c1 ^ rk[2 * r], n2 = hi0 ^ c3 ^ rk[2 * r + 1];
+		c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+	}
+	return make_uint4(c0, c1, c2, c3);
+}
+__host__ __device__ inline void philox_round_keys(unsigned long long seed, uint32_t (&rk)[20]) {
+	uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+	for (int r = 0; r < 10; ++r) { rk[2 * r] = k0; rk[2 * r + 1] = k1; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+}
+
+// kRK: the round keys come from `rk` (see philox4x32_10_rk) instead of (k0, k1); the members a build does not use cost nothing.
+template <bool kRK>
+struct PathRngT {
 	uint32_t pixel, sample, draw, k0, k1;
+	const uint32_t* rk;
 	uint4 buf;
+	__device__ __forceinline__ uint4 block(uint32_t b) const {
+		if (kRK) return philox4x32_10_rk(pixel, sample, b, 0u, rk);
+		return philox4x32_10(pixel, sample, b, 0u, k0, k1);
+	}
 	__device__ __forceinline__ void start(uint64_t seed, uint32_t pixel_, uint32_t sample_) {
 		pixel = pixel_; sample = sample_; draw = 0; k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32);
 	}
 	__device__ __forceinline__ uint32_t next_u32() {
 		uint32_t w = draw & 3u;
-		if (w == 0) buf = philox4x32_10(pixel, sample, draw >> 2, 0u, k0, k1);
+		if (w == 0) buf = block(draw >> 2);
 		++draw;
 		return w == 0 ? buf.x : (w == 1 ? buf.y : (w == 2 ? buf.z : buf.w));
 	}
@@ -182,7 +207,7 @@ struct PathRng {
 #if GS_RNG_TAKE
 		const uint32_t w = draw & 3u;
 		const uint4 o = buf;
-		if (w == 0u || w + (uint32_t)K > 4u) buf = philox4x32_10(pixel, sample, (draw + 3u) >> 2, 0u, k0, k1);  // the block after `o`, or of draw itself when w == 0
+		if (w == 0u || w + (uint32_t)K > 4u) buf = block((draw + 3u) >> 2);  // the block after `o`, or of draw itself when w == 0
 		const uint4 n = buf;
 		const bool w0 = w == 0u, w1 = w == 1u, w2 = w == 2u;
 		out[0] = w0 ? n.x : (w1 ? o.y : (w2 ? o.z : o.w));
@@ -200,6 +225,7 @@ struct PathRng {
 	__device__ __forceinline__ double next_f64() { return (double)next_u32() * (1.0 / 4294967296.0); }       // the oracle's value exactly
 	__device__ __forceinline__ void ensure(int) {}  // blocks are computed where a draw needs one (see PathRngW)
 };
+using PathRng = PathRngT<false>;
 
 // The same stream -- draw k of a path is word k & 3 of block k >> 2 -- with the blocks computed AHEAD, at a point where the warp's
 // lanes are together, instead of at whichever of a dozen divergent draw sites a lane's counter happens to cross a block boundary

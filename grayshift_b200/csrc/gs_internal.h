@@ -27,6 +27,7 @@ struct RenderParams {
 	unsigned round0;
 	bool small_scene;                      // nodes + primitives <= kSmallSceneBytes: the launch takes the 6-CTAs-per-SM build
 	bool wide;                             // traverse sc.nodes8 (eight-wide tree) instead of sc.nodes
+	uint32_t philox_rk[20];                // the ten Philox round-key pairs of `seed` (filled by launch_render_fixed)
 };
 
 struct AdaptiveTailParams {  // the last few pixels: one warp per pixel runs the rest of its batch loop (adaptive_tail_kernel)

@@ -636,7 +636,10 @@ __device__ __forceinline__ void noise_apply_deferred(const DeviceScene& sc, cons
 // One whole level, run to completion (adaptive kernel and the per-path hooks).
 // kernel variant -> tuning of the shading code: bit 0 Perlin gradients from the CTA's table, bit 1 draws taken together.
 // Small-scene kernels (kF & 8) both, eight-wide kernels (kF & 16) the draws, the others neither (see the measurements above).
-__host__ __device__ constexpr int tune_of(int kF) { return (kF & 8) ? 3 : ((kF & 16) ? 2 : 0); }
+#ifndef GS_TAKE_ALL
+#define GS_TAKE_ALL 0  // A/B knob: draws taken together in every kernel variant
+#endif
+__host__ __device__ constexpr int tune_of(int kF) { return ((kF & 8) ? 3 : ((kF & 16) ? 2 : 0)) | (GS_TAKE_ALL ? 2 : 0); }
 
 template <int kF>
 __device__ __forceinline__ bool path_step(const DeviceScene& sc, const DCamera& cam, const uint8_t* __restrict__ perm, PathState& st,

@@ -64,6 +64,11 @@ static_assert(kTopNodes <= kNodePad, "gs_scene_create pads the node array to kNo
 #define GS_RNG_WINDOW 0   // the megakernel's paths draw from a two-block window in shared memory, filled once per level at a converged point
                           // (PathRngW, gs_device.cuh); 0 = one block in registers, computed at the draw that needs it
 #endif
+#ifndef GS_PHILOX_RK
+#define GS_PHILOX_RK 0    // 1 = Philox round keys from the parameter block, rounds unrolled (philox4x32_10_rk: 4 instructions per round instead of 7.5);
+                          // 0 = key schedule in registers, rolled loop.  Measured (profiles/r02_v15_ab.log): +2 % config 3, +4 % scene 3, +2 % config 2,
+                          // but -15 % on config 4 -- its ten inlined copies grow by 500 instructions and the kernel falls off the instruction cache
+#endif
 #ifndef GS_NODE_UNROLL2
 #define GS_NODE_UNROLL2 0
 #endif
@@ -114,7 +119,8 @@ __global__ void GS_RENDER_BOUNDS(kF) render_fixed_kernel(const __grid_constant__
 	PathStateT<PathRngW<kBlock>> st;
 	st.rng.win = &s_rng[0][threadIdx.x];
 #else
-	PathState st;
+	PathStateT<PathRngT<GS_PHILOX_RK != 0>> st;
+	st.rng.rk = P.philox_rk;
 #endif
 	int state = kDead;
 	Trav tv;
@@ -740,7 +746,9 @@ static int fixed_blocks_per_sm(int variant) {
 
 int render_fixed_blocks_per_sm(bool count_nodes, bool triangles) { return fixed_blocks_per_sm((count_nodes ? 1 : 0) | (triangles ? 2 : 0)); }
 
-cudaError_t launch_render_fixed(const RenderParams& p, int sm_count, bool count_nodes, bool triangles, cudaStream_t stream) {
+cudaError_t launch_render_fixed(const RenderParams& p_in, int sm_count, bool count_nodes, bool triangles, cudaStream_t stream) {
+	RenderParams p = p_in;
+	philox_round_keys(p.seed, p.philox_rk);
 	const int variant = fixed_variant(p, count_nodes, triangles);
 	const int per_sm = fixed_blocks_per_sm(variant);
 	unsigned long long warps_needed = (p.total_items + 31ull) / 32ull;  // adaptive: total_items = the upper bound (every listed pixel)
