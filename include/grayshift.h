@@ -19,6 +19,12 @@
  * otherwise with a thread-local message in gs_last_error().  Nothing aborts or throws across
  * this boundary.  All geometry is f64, world space, as in the reference (util/vec3.rs:6-10).
  * There is NO CPU fallback: without a CUDA device every compute entry returns GS_ERR_NO_DEVICE.
+ *
+ * Concurrency: handles are independent of each other, and any number of threads may work on DIFFERENT
+ * gs_scene handles at once (the worker pool, the staging buffers and the error string are shared
+ * safely).  One handle is not re-entrant: calls on it must come from one thread at a time, like
+ * `&mut self`.  Asynchronous renders of one handle may overlap on different CUDA streams; each launch
+ * takes the next of 256 work counters of the handle, so at most 256 of them may be in flight at once.
  */
 #ifndef GRAYSHIFT_H
 #define GRAYSHIFT_H
