@@ -368,3 +368,37 @@ def test_noise_textures_evaluated_by_the_warp_match_the_per_lane_evaluation(name
     same = np.isclose(got, per_path, rtol=1e-3, atol=1e-5).all(axis=1).mean()
     assert same > 0.998, f"only {same:.4f} of the pixels agree between the megakernel and the per-path hook"
     assert abs(got.mean() - per_path.mean()) <= 1e-4 * per_path.mean()
+
+
+def test_deferred_noise_on_lights_checkers_and_media(tmp_path):
+    """The three ways a NoiseTexture reaches the megakernel's deferred evaluation besides a Lambertian albedo: as a DiffuseLight's
+    emission (added, not multiplied, and the path ends there), nested in a CheckeredTexture, and as the albedo of a medium's
+    Isotropic phase function.  Megakernel image against the per-path hook (inline evaluation), then both against the oracle."""
+    g = Graph()
+    marble = g.noise(4.0)
+    lamp = g.quad([-2, 3.5, -2], [4, 0, 0], [0, 0, 4], g.light(marble))
+    floor = g.quad([-30, -1, -30], [60, 0, 0], [0, 0, 60], g.lambertian(g.checker(0.8, marble, g.solid([0.8, 0.3, 0.2]))))
+    ball = g.sphere([0, 0.2, 0], 1.2, g.lambertian(marble))
+    smoke = g.medium(g.sphere([2.6, 0.3, 0.5], 1.0, g.lambertian_color([1, 1, 1])), 0.9, g.isotropic(marble))
+    g.camera(aspect=1.5, width=96, batch=8, depth=12, vfov=45.0, look_from=(1, 2.5, 7), look_at=(0.5, 0.3, 0))
+    g.background_solid([0.25, 0.3, 0.4])
+    p = g.write(str(tmp_path / "noise.gsg"), g.bvh([lamp, floor, ball, smoke]))
+    host, ora = gs.HostScene.load(p), orc.OracleScene.load(p)
+    dev = gs.DeviceScene(host)
+    spp = 8
+    rgb, counts, _ = dev.render(seed=6)
+    n = dev.width * dev.height
+    assert np.all(counts == spp)
+    px = np.repeat(np.arange(n, dtype=np.uint32), spp)
+    sm = np.tile(np.arange(spp, dtype=np.uint32), n)
+    per_path = dev.path_radiance(seed=6, pixels=px, samples=sm).astype(np.float64)
+    got = rgb.reshape(n, 3).astype(np.float64)
+    want = per_path.reshape(n, spp, 3).mean(axis=1)
+    same = np.isclose(got, want, rtol=1e-3, atol=1e-5).all(axis=1).mean()
+    assert same > 0.998, f"only {same:.4f} of the pixels agree between the megakernel and the per-path hook"
+    # media scenes are compared with the oracle statistically (the device draws a medium's free flight before the traversal)
+    a, _, _, _ = ora.render(seed=7, rng=orc.OracleScene.PHILOX)
+    b, _, _, _ = ora.render(seed=8, rng=orc.OracleScene.PHILOX)
+    err = np.sqrt(np.mean((tonemap_np(rgb.astype(np.float64)) - tonemap_np(a)) ** 2))
+    noise = np.sqrt(np.mean((tonemap_np(b) - tonemap_np(a)) ** 2))
+    assert err <= 1.25 * noise, (err, noise)
