@@ -452,11 +452,24 @@ __device__ __forceinline__ DTriangle load_triangle(const DTriangle* __restrict__
 	return DTriangle{a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y, e.x, e.y, f.x, f.y};
 }
 
+#ifndef GS_APPROX_RCP
+#define GS_APPROX_RCP 1  // 1 / d of the slab test with rcp.approx.ftz.f32 (one MUFU, relative error <= 2^-23) instead of the IEEE division
+                         // (eight instructions plus a slow path), three times per ray and traversal phase: +2.7 % config 4, +2.0 % C3, +1.4 % C1,
+                         // +0.9 % C5 (profiles/r02_v15_ab.log section 9).  The boxes' padding budgets a full 2^-23 for the reciprocal
+                         // (scene_layout.cu, "fp32 error budget"), so the test stays conservative; the parity kernel (GS_EXACT_F64) keeps the division.
+                         // (ftz: 1 / d underflows to 0 only for |d| > 8.5e37)
+#endif
 __device__ __forceinline__ float safe_rcp(float d) {
 	// 1/0 = inf in the reference (AABB.rs:64); a huge finite inverse orders the slabs identically without NaNs
 	// (1e25 keeps origin * inverse finite for any origin the padded boxes allow)
 	float ad = fabsf(d);
+#if GS_APPROX_RCP && defined(__CUDA_ARCH__) && !defined(GS_EXACT_F64)
+	float r;
+	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+	return ad < 1e-25f ? copysignf(1e25f, d) : r;
+#else
 	return ad < 1e-25f ? copysignf(1e25f, d) : 1.0f / d;
+#endif
 }
 
 // ------------------------------------------------------------------------------------------

@@ -951,7 +951,7 @@ int layout_scene(gs_scene* s, const gs_scene_desc* d) {
 // ---- node arrays --------------------------------------------------------------------------------------------
 // fp32 error budget of a slab distance fma(plane, 1/d, -o/d): origin and plane rounding (<= 1 ulp at origin_limit),
 // subtraction, reciprocal and product (relative 2^-23 each over distances <= 2*origin_limit) -> 8 ulp(origin_limit) is
-// safe.  The wide nodes add the rounding of the quantised decode (two more FMAs): 12 ulp, plus 1/64 of a grid step
+// safe.  (The render kernels take the reciprocal from rcp.approx.ftz.f32, whose error bound is that 2^-23; gs_device.cuh safe_rcp.)  The wide nodes add the rounding of the quantised decode (two more FMAs): 12 ulp, plus 1/64 of a grid step
 // for the bias constant of Trav8::qf (its own error is 2^-9 of a step).
 static double pad_for(double origin_limit, int ulps) {
 	const float lim = (float)origin_limit;
