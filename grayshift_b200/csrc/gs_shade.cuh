@@ -20,6 +20,29 @@ __device__ __forceinline__ f3 unit(f3 a) { float inv = rsqrtf(dot(a, a)); return
 
 constexpr float kPi = 3.14159265358979323846f;
 
+// fp32 square root and reciprocal of the shading code.  The IEEE forms (sqrtf, 1.0f / x) are a MUFU plus a Newton step plus a
+// test for a slow path that lives in the kernel as a called function; the twelve call sites cost the config-4 kernel its last
+// 72 B of spills.  The approximate instructions (<= 1 ulp for rcp, <= 2 ulp for sqrt) are written out as PTX so that every
+// kernel variant computes the same bits (nvcc's -prec-sqrt=false / -prec-div=false left the binary-tree and the eight-wide kernels
+// with slightly different paths).  Shading is fp32 on f64 hit points and compared with the oracle to 2e-3 per path.
+#ifndef GS_FAST_F32
+#define GS_FAST_F32 1
+#endif
+__device__ __forceinline__ float sqrt_f32(float x) {
+#if GS_FAST_F32 && defined(__CUDA_ARCH__)
+	float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+#else
+	return sqrtf(x);
+#endif
+}
+__device__ __forceinline__ float rcp_f32(float x) {
+#if GS_FAST_F32 && defined(__CUDA_ARCH__)
+	float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+#else
+	return 1.0f / x;
+#endif
+}
+
 // ---- random helpers, util.rs:18-60 ---------------------------------------------------------------
 // Two forms of the three functions that draw several numbers in a row: *_single draws them one by one, *_take takes them
 // together (PathRng::take: at most one Philox block per call site).  Same values.  Measured on the A/B harness
@@ -42,8 +65,8 @@ __device__ __forceinline__ f3 random_cosine_direction_single(Rng& rng) {  // uti
 	float r2 = rng.next_f32();
 	float s, c;
 	sincospif(2.0f * r1, &s, &c);
-	float q = sqrtf(sqrtf(r2));
-	return mk3(c * q, s * q, sqrtf(1.0f - r2));
+	float q = sqrt_f32(sqrt_f32(r2));
+	return mk3(c * q, s * q, sqrt_f32(1.0f - r2));
 }
 
 // ---- Camera::get_ray, camera.rs:204-226 (f64, same draws as the oracle) --------------------------
@@ -95,8 +118,8 @@ __device__ __forceinline__ f3 random_cosine_direction_take(Rng& rng) {  // util.
 	float r2 = PathRng::to_f32(u[1]);
 	float s, c;
 	sincospif(2.0f * r1, &s, &c);
-	float q = sqrtf(sqrtf(r2));
-	return mk3(c * q, s * q, sqrtf(1.0f - r2));
+	float q = sqrt_f32(sqrt_f32(r2));
+	return mk3(c * q, s * q, sqrt_f32(1.0f - r2));
 }
 
 // ---- Camera::get_ray, camera.rs:204-226 (f64, same draws as the oracle) --------------------------
@@ -377,12 +400,12 @@ __device__ __forceinline__ bool shade(const DeviceScene& sc, const uint8_t* __re
 		}
 		case 2: {  // Dielectric
 			float ir = m1.y;
-			float ri = s.front ? 1.0f / ir : ir;
+			float ri = s.front ? rcp_f32(ir) : ir;
 			f3 ud = unit(d_in);
 			float cos_theta = fminf(-dot(ud, s.n), 1.0f);
-			float sin_theta = sqrtf(fmaxf(1.0f - cos_theta * cos_theta, 0.0f));
+			float sin_theta = sqrt_f32(fmaxf(1.0f - cos_theta * cos_theta, 0.0f));
 			bool cannot_refract = ri * sin_theta > 1.0f;
-			float r0 = (1.0f - ri) / (1.0f + ri);
+			float r0 = (1.0f - ri) * rcp_f32(1.0f + ri);
 			r0 = r0 * r0;
 			float m = 1.0f - cos_theta;
 			float reflectance = r0 + (1.0f - r0) * (m * m * m * m * m);
@@ -391,7 +414,7 @@ __device__ __forceinline__ bool shade(const DeviceScene& sc, const uint8_t* __re
 			else {  // Vec3::refract, vec3.rs:57-62
 				float ct = fminf(dot(s.n, -ud), 1.0f);
 				f3 perp = (ud + s.n * ct) * ri;
-				f3 par = s.n * (-sqrtf(fabsf(1.0f - dot(perp, perp))));
+				f3 par = s.n * (-sqrt_f32(fabsf(1.0f - dot(perp, perp))));
 				d_out = perp + par;
 			}
 			atten = mk3(1.f, 1.f, 1.f);
@@ -567,7 +590,7 @@ __device__ __forceinline__ bool segment_shade(const DeviceScene& sc, const DCame
 			if ((h.ref >> kRefKindShift) == kKindMovingSphere) { double4 p = sc.sph_path[index]; cx += ray.time * p.x; cy += ray.time * p.y; cz += ray.time * p.z; }
 			// outward_normal = (p - c) / r with the SIGNED radius (sphere.rs:91: a negative radius turns the normal inward, the
 			// hollow-glass trick); difference in f64, quotient in f32
-			const float inv_r = 1.0f / (float)sp.r;
+			const float inv_r = rcp_f32((float)sp.r);
 			n_out = mk3((float)(s.px - cx) * inv_r, (float)(s.py - cy) * inv_r, (float)(s.pz - cz) * inv_r);
 			s.is_sphere = true; s.u = 0.f; s.v = 0.f; s.quad_index = -1; s.sphere_index = (int)index;
 			s.material = __ldg(sc.sph_aux + index).x;

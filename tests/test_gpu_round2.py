@@ -86,7 +86,10 @@ def test_both_trees_render_the_same_paths(name, kw):
     dev.set_option("bvh_width", 8)
     b, cb, sb = dev.render(seed=5)
     assert np.array_equal(ca, cb) and sa.paths == sb.paths
-    assert abs(int(sa.rays) - int(sb.rays)) <= 1e-4 * int(sa.rays)
+    # (config 1 and scene 7 trace exactly the same rays with both kernels; on config 4 a few paths in 10^4 part ways at a decision
+    # boundary -- the two kernel variants are compiled separately and round a handful of fp32 shading operations differently --
+    # and a path that parts ways runs to another depth: 3e-5 of the rays with IEEE fp32 square roots, 2.3e-4 with the approximate ones)
+    assert abs(int(sa.rays) - int(sb.rays)) <= 5e-4 * int(sa.rays)
     same = np.isclose(a, b, rtol=1e-3, atol=1e-5).all(axis=2).mean()
     assert same > 0.998, f"only {same:.4f} of the pixels agree between the binary and the eight-wide tree"
 
