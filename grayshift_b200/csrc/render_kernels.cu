@@ -65,9 +65,11 @@ static_assert(kTopNodes <= kNodePad, "gs_scene_create pads the node array to kNo
                           // (PathRngW, gs_device.cuh); 0 = one block in registers, computed at the draw that needs it
 #endif
 #ifndef GS_PHILOX_RK
-#define GS_PHILOX_RK 0    // 1 = Philox round keys from the parameter block, rounds unrolled (philox4x32_10_rk: 4 instructions per round instead of 7.5);
-                          // 0 = key schedule in registers, rolled loop.  Measured (profiles/r02_v15_ab.log): +2 % config 3, +4 % scene 3, +2 % config 2,
-                          // but -15 % on config 4 -- its ten inlined copies grow by 500 instructions and the kernel falls off the instruction cache
+#define GS_PHILOX_RK 0    // Philox round keys from the parameter block, rounds unrolled (philox4x32_10_rk: 4 instructions per round instead of 7.5):
+                          // 1 = every kernel variant, 2 = the small-scene variants (kF & 8) only, 0 = none (key schedule in registers, rolled loop).
+                          // Measured (profiles/r02_v15_ab.log sections 6 and 12): +3.9 % config 1, +1.1 % config 3, +4 % scene 3, +2 % config 2 -- but
+                          // -7...-15 % on config 4, whose kernel falls off the instruction cache with ten unrolled copies; and on the final code the
+                          // small-scene variants split: +3.9 % C1, +1.2 % C3, but -6.7 % C2, -2.3 % scene 5 (204 B of spills).  Left off.
 #endif
 #ifndef GS_NODE_UNROLL2
 #define GS_NODE_UNROLL2 0
@@ -119,7 +121,7 @@ __global__ void GS_RENDER_BOUNDS(kF) render_fixed_kernel(const __grid_constant__
 	PathStateT<PathRngW<kBlock>> st;
 	st.rng.win = &s_rng[0][threadIdx.x];
 #else
-	PathStateT<PathRngT<GS_PHILOX_RK != 0>> st;
+	PathStateT<PathRngT<GS_PHILOX_RK == 1 || (GS_PHILOX_RK == 2 && (kF & 8) != 0)>> st;
 	st.rng.rk = P.philox_rk;
 #endif
 	int state = kDead;
